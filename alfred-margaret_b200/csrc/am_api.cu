@@ -1,0 +1,504 @@
+// am_api.cu -- the C ABI of libam_b200 (include/am_b200.h).
+//
+// Host orchestration only: automaton upload, workspaces, launch order, result readback.
+// There is deliberately NO CPU fallback: without an sm_100 device every compute entry point
+// fails with AM_E_NODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "am_api_internal.h"
+
+namespace am {
+
+thread_local std::string g_last_error;
+thread_local uint64_t g_last_passes = 0;
+
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return AM_E_CUDA;
+}
+
+static int usable_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; d++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
+
+// ---- device memory helpers ---------------------------------------------------------------------------
+template <class T>
+static int upload(am_automaton* a, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(automaton)");
+  a->dev_allocs.push_back(p);
+  if (!v.empty()) {
+    e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(automaton)");
+  }
+  *out = static_cast<const T*>(p);
+  return AM_OK;
+}
+
+Workspace::~Workspace() {
+  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b})
+    if (p) cudaFree(p);
+  if (h_scalars) cudaFreeHost(h_scalars);
+}
+
+static int ws_grow(void** p, size_t* cap, size_t need, const char* what) {
+  if (*cap >= need) return AM_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  size_t want = need + need / 8 + 256;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) { cudaGetLastError(); g_last_error = std::string("cudaMalloc(") + what + ") of " + std::to_string(want) + " bytes failed"; return AM_E_OOM; }
+  *cap = want;
+  return AM_OK;
+}
+int Workspace::need_keys(uint64_t n) {
+  int rc = ws_grow((void**)&keys_a, &keys_a_bytes, n * 8, "keys");
+  if (rc) return rc;
+  return ws_grow((void**)&keys_b, &keys_b_bytes, n * 8, "keys");
+}
+int Workspace::need_sort_temp(size_t b) { return ws_grow(&sort_temp, &sort_temp_bytes_, b, "sort temp"); }
+int Workspace::need_text(uint64_t n) { return ws_grow((void**)&text, &text_bytes, n + 64, "text"); }
+int Workspace::need_matches(uint64_t n) { return ws_grow((void**)&matches, &matches_bytes, n * sizeof(am_match), "matches"); }
+int Workspace::need_aux(uint64_t a_bytes, uint64_t b_bytes) {
+  int rc = ws_grow((void**)&aux_a, &aux_a_bytes, a_bytes, "aux");
+  if (rc) return rc;
+  return ws_grow((void**)&aux_b, &aux_b_bytes, b_bytes, "aux");
+}
+
+Workspace* acquire_ws(const am_automaton* ca) {
+  am_automaton* a = const_cast<am_automaton*>(ca);
+  {
+    std::lock_guard<std::mutex> g(a->ws_mutex);
+    if (!a->ws_pool.empty()) { Workspace* w = a->ws_pool.back(); a->ws_pool.pop_back(); return w; }
+  }
+  Workspace* w = new Workspace();
+  if (cudaMalloc((void**)&w->d_scalars, 256) != cudaSuccess || cudaMallocHost((void**)&w->h_scalars, 256) != cudaSuccess) {
+    cudaGetLastError(); delete w; return nullptr;
+  }
+  return w;
+}
+void release_ws(const am_automaton* ca, Workspace* w) {
+  am_automaton* a = const_cast<am_automaton*>(ca);
+  std::lock_guard<std::mutex> g(a->ws_mutex);
+  a->ws_pool.push_back(w);
+}
+
+int check_ready(const am_automaton* a) {
+  if (!a) return fail(AM_E_BADARG, "automaton is null");
+  if (a->device < 0) return fail(AM_E_NODEVICE, "automaton was built without a device (host image only); there is no CPU fallback");
+  cudaError_t e = cudaSetDevice(a->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  return AM_OK;
+}
+
+static int bitlen(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
+
+// Launch one scan in `mode`; COUNT/EMIT totals land in ws->d_scalars[0], the ANY flag in d_scalars[8..].
+int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st) {
+  if (t.report_begin > t.text_len) return fail(AM_E_BADARG, "report_begin > text_len");
+  if (t.text_len > 0 && !t.dev_text) return fail(AM_E_BADARG, "dev_text is null");
+  if (bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits > 64) return fail(AM_E_UNSUPPORTED, "position and needle rank do not fit a 64-bit sort key");
+  ScanArgs sa;
+  sa.text = static_cast<const uint8_t*>(t.dev_text);
+  sa.text_len = t.text_len; sa.report_begin = t.report_begin; sa.pos_base = t.pos_base;
+  sa.d_count = reinterpret_cast<unsigned long long*>(ws->d_scalars);
+  sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
+  sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
+  cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  return AM_OK;
+}
+
+static int read_scalars(Workspace* ws, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 16, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scalars)");
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "scan kernel");
+  return AM_OK;
+}
+
+// Scan in EMIT mode and sort; on return ws->keys_b[0..*n) holds the sorted keys.
+int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n) {
+  uint64_t span = t.text_len - std::min(t.report_begin, t.text_len);
+  int rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
+  if (rc) return rc;
+  for (int attempt = 0;; attempt++) {
+    rc = launch_scan(a, ws, t, MODE_EMIT, st);
+    if (rc) return rc;
+    rc = read_scalars(ws, st);
+    if (rc) return rc;
+    *n = *reinterpret_cast<uint64_t*>(ws->h_scalars);
+    if (*n <= ws->keys_a_bytes / 8) break;
+    if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
+    rc = ws->need_keys(*n);  // exact size is now known: rescan
+    if (rc) return rc;
+  }
+  if (*n == 0) return AM_OK;
+  const int end_bit = std::min(64, bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits);
+  size_t tb = sort_temp_bytes(*n, end_bit);
+  rc = ws->need_sort_temp(tb);
+  if (rc) return rc;
+  cudaError_t e = sort_keys(ws->sort_temp, tb, ws->keys_a, ws->keys_b, *n, end_bit, st);
+  if (e != cudaSuccess) return cuda_fail(e, "radix sort");
+  return AM_OK;
+}
+
+// ---- L1 text substrate helpers (host) -----------------------------------------------------------------------------
+static inline int dec(const uint8_t* d, int64_t i, int64_t n, uint32_t* cp) {  // decodeN, Utf8.hs:344-350
+  uint32_t c0 = d[i];
+  if (c0 < 0xC0) { *cp = c0; return 1; }
+  uint32_t c1 = i + 1 < n ? d[i + 1] : 0;
+  if (c0 < 0xE0) { *cp = ((c0 & 0x1F) << 6) | (c1 & 0x3F); return 2; }
+  uint32_t c2 = i + 2 < n ? d[i + 2] : 0;
+  if (c0 < 0xF0) { *cp = ((c0 & 0xF) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F); return 3; }
+  uint32_t c3 = i + 3 < n ? d[i + 3] : 0;
+  *cp = ((c0 & 7) << 18) | ((c1 & 0x3F) << 12) | ((c2 & 0x3F) << 6) | (c3 & 0x3F);
+  return 4;
+}
+static inline int enc(uint32_t c, uint8_t* o) {  // unicode2utf8, Utf8.hs:154-160
+  if (c < 0x80) { o[0] = (uint8_t)c; return 1; }
+  if (c < 0x800) { o[0] = 0xC0 | (c >> 6); o[1] = 0x80 | (c & 0x3F); return 2; }
+  if (c < 0x10000) { o[0] = 0xE0 | (c >> 12); o[1] = 0x80 | ((c >> 6) & 0x3F); o[2] = 0x80 | (c & 0x3F); return 3; }
+  o[0] = 0xF0 | (c >> 18); o[1] = 0x80 | ((c >> 12) & 0x3F); o[2] = 0x80 | ((c >> 6) & 0x3F); o[3] = 0x80 | (c & 0x3F); return 4;
+}
+
+int lower_utf8_host(const LowerTable& lt, const uint8_t* in, int64_t len, std::vector<uint8_t>* out) {
+  out->clear(); out->reserve((size_t)len + 8);
+  int64_t i = 0;
+  while (i < len) {
+    uint32_t cp; int k = dec(in, i, len, &cp);
+    uint8_t b[4]; int m = enc(lt.lower(cp), b);
+    out->insert(out->end(), b, b + m);
+    i += k;
+  }
+  return AM_OK;
+}
+
+
+}  // namespace am
+
+using namespace am;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* am_last_error(void) { return g_last_error.c_str(); }
+int am_abi_version(void) { return AM_ABI_VERSION; }
+int am_device_count(void) { return usable_device_count(); }
+
+int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower, const am_options* opts,
+                       am_automaton** out) {
+  if (!out) return fail(AM_E_BADARG, "out is null");
+  *out = nullptr;
+  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table (it may be empty)");
+  am_automaton* a = new am_automaton();
+  std::string err;
+  int rc = build_host_automaton(needles, n, cs, lower, &a->host, &err);
+  if (rc != AM_OK) { delete a; return fail(rc, err); }
+  const int want_dev = opts ? opts->device : -1;
+  const int force = opts ? opts->force_kernel : 0;
+  HostAutomaton& H = a->host;
+  a->kernel_kind = (force != 1 && cs == AM_CASE_SENSITIVE && H.q > 0) ? 2 : 1;
+  if (force == 2 && a->kernel_kind != 2) { delete a; return fail(AM_E_UNSUPPORTED, "filter kernel not applicable to this needle set"); }
+  if (want_dev == -2) { a->device = -1; *out = a; return AM_OK; }  // host image only (tests / introspection)
+
+  if (usable_device_count() == 0) { delete a; return fail(AM_E_NODEVICE, "no sm_100 CUDA device; libam_b200 has no CPU fallback"); }
+  int dev = want_dev;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) { delete a; return cuda_fail(e, "cudaSetDevice"); }
+  a->device = dev;
+
+  DevAutomaton& D = a->dev;
+  std::memset(&D, 0, sizeof D);
+  if (H.filter.empty()) { H.filter.assign(FILTER_WORDS, 0); }
+  if (H.filter2.empty()) { H.filter2.assign((1u << FILTER2_LOG2_BITS) / 32, 0); }
+  if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE}); H.jump_mask = 15; }
+  if ((rc = upload(a, H.dense, &D.dense)) || (rc = upload(a, H.fail, &D.fail)) || (rc = upload(a, H.edges, &D.edges)) ||
+      (rc = upload(a, H.jump, &D.jump)) || (rc = upload(a, H.filter, &D.filter)) || (rc = upload(a, H.filter2, &D.filter2)) ||
+      (rc = upload(a, H.own_off, &D.own_off)) || (rc = upload(a, H.own_rank, &D.own_rank)) ||
+      (rc = upload(a, H.first_out, &D.first_out)) || (rc = upload(a, H.next_out, &D.next_out)) ||
+      (rc = upload(a, H.chain_count, &D.chain_count)) || (rc = upload(a, H.id_of_rank, &D.id_of_rank)) ||
+      (rc = upload(a, H.len_of_rank, &D.len_of_rank)) || (rc = upload(a, H.lower.stage1, &D.lower1)) ||
+      (rc = upload(a, H.lower.stage2, &D.lower2))) {
+    am_automaton_free(a);
+    return rc;
+  }
+  D.dense_states = H.dense_states; D.edge_mask = H.edge_mask; D.jump_mask = H.jump_mask;
+  D.q = H.q; D.qmask = qgram_mask(H.q); D.min_len = H.min_len; D.max_len = H.max_len; D.rank_bits = H.rank_bits;
+  D.num_states = H.num_states; D.num_needles = H.num_needles;
+  D.ignore_case = cs == AM_IGNORE_CASE; D.halo = (uint32_t)H.halo_bytes;
+  *out = a;
+  return AM_OK;
+}
+
+void am_automaton_free(am_automaton* a) {
+  if (!a) return;
+  if (a->device >= 0) cudaSetDevice(a->device);
+  for (Workspace* w : a->ws_pool) delete w;
+  for (void* p : a->dev_allocs) cudaFree(p);
+  delete a;
+}
+
+int am_automaton_info(const am_automaton* a, uint64_t* num_states, uint64_t* max_needle_bytes, uint64_t* halo_bytes, int* kernel_kind) {
+  if (!a) return fail(AM_E_BADARG, "automaton is null");
+  if (num_states) *num_states = a->host.num_states;
+  if (max_needle_bytes) *max_needle_bytes = a->host.max_len;
+  if (halo_bytes) *halo_bytes = a->host.halo_bytes;
+  if (kernel_kind) *kernel_kind = a->kernel_kind;
+  return AM_OK;
+}
+
+// ---- device-resident entry points -------------------------------------------------------------------------
+int am_count_matches_dev(const am_automaton* a, am_dev_text t, void* stream, uint64_t* out_count) {
+  int rc = check_ready(a); if (rc) return rc;
+  if (!out_count) return fail(AM_E_BADARG, "out_count is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_scan(a, ws, t, MODE_COUNT, st);
+  if (!rc) rc = read_scalars(ws, st);
+  if (!rc) *out_count = *reinterpret_cast<uint64_t*>(ws->h_scalars);
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_contains_any_dev(const am_automaton* a, am_dev_text t, void* stream, int* out_bool) {
+  int rc = check_ready(a); if (rc) return rc;
+  if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_scan(a, ws, t, MODE_ANY, st);
+  if (!rc) rc = read_scalars(ws, st);
+  if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_find_all_dev(const am_automaton* a, am_dev_text t, void* stream, am_match* dev_out, size_t cap, uint64_t* n_found) {
+  int rc = check_ready(a); if (rc) return rc;
+  if (!n_found) return fail(AM_E_BADARG, "n_found is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint64_t n = 0;
+  rc = find_all_sorted(a, ws, t, st, &n);
+  if (!rc) {
+    *n_found = n;
+    if (n > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
+    else if (n > 0) {
+      if (!dev_out) rc = fail(AM_E_BADARG, "dev_out is null");
+      else {
+        cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, dev_out, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "unpack");
+      }
+    }
+  }
+  release_ws(a, ws);
+  return rc;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------------
+static int check_slice(const am_u8slice& s) {
+  if (s.len < 0 || s.off < 0 || (s.len > 0 && !s.ptr)) return fail(AM_E_BADARG, "bad text slice");
+  return AM_OK;
+}
+static int upload_text(Workspace* ws, const am_u8slice& hay, cudaStream_t st, am_dev_text* t) {
+  int rc = ws->need_text((uint64_t)hay.len);
+  if (rc) return rc;
+  if (hay.len > 0) {
+    cudaError_t e = cudaMemcpyAsync(ws->text, hay.ptr + hay.off, (size_t)hay.len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D text)");
+  }
+  t->dev_text = ws->text; t->text_len = (uint64_t)hay.len; t->report_begin = 0; t->pos_base = 0;
+  return AM_OK;
+}
+
+int am_count_matches(const am_automaton* a, am_u8slice hay, uint64_t* out_count) {
+  int rc = check_ready(a); if (rc) return rc;
+  if ((rc = check_slice(hay))) return rc;
+  if (!out_count) return fail(AM_E_BADARG, "out_count is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  am_dev_text t;
+  rc = upload_text(ws, hay, 0, &t);
+  if (!rc) rc = launch_scan(a, ws, t, MODE_COUNT, 0);
+  if (!rc) rc = read_scalars(ws, 0);
+  if (!rc) *out_count = *reinterpret_cast<uint64_t*>(ws->h_scalars);
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_contains_any(const am_automaton* a, am_u8slice hay, int* out_bool) {
+  int rc = check_ready(a); if (rc) return rc;
+  if ((rc = check_slice(hay))) return rc;
+  if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  am_dev_text t;
+  rc = upload_text(ws, hay, 0, &t);
+  if (!rc) rc = launch_scan(a, ws, t, MODE_ANY, 0);
+  if (!rc) rc = read_scalars(ws, 0);
+  if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_find_all(const am_automaton* a, am_u8slice hay, am_match* out, size_t cap, uint64_t* n_found) {
+  int rc = check_ready(a); if (rc) return rc;
+  if ((rc = check_slice(hay))) return rc;
+  if (!n_found) return fail(AM_E_BADARG, "n_found is null");
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  am_dev_text t;
+  uint64_t n = 0;
+  rc = upload_text(ws, hay, 0, &t);
+  if (!rc) rc = find_all_sorted(a, ws, t, 0, &n);
+  if (!rc) {
+    *n_found = n;
+    if (n > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
+    else if (n > 0) {
+      if (!out) rc = fail(AM_E_BADARG, "out is null");
+      else if (!(rc = ws->need_matches(n))) {
+        cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, ws->matches, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, ws->matches, n * sizeof(am_match), cudaMemcpyDeviceToHost, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) rc = cuda_fail(e, "unpack / D2H");
+      }
+    }
+  }
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_contains_all(const am_automaton* a, am_u8slice hay, int* out_bool) {
+  // Searcher.containsAll (Searcher.hs:173-187): every needle id must be seen at least once.
+  int rc = check_ready(a); if (rc) return rc;
+  if ((rc = check_slice(hay))) return rc;
+  if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
+  const uint64_t nn = a->host.num_needles;
+  if (nn == 0) { *out_bool = 1; return AM_OK; }
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  am_dev_text t;
+  uint64_t n = 0;
+  rc = upload_text(ws, hay, 0, &t);
+  if (!rc) rc = find_all_sorted(a, ws, t, 0, &n);
+  if (!rc) {
+    std::vector<uint64_t> keys(n);
+    if (n) {
+      cudaError_t e = cudaMemcpy(keys.data(), ws->keys_b, n * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = cuda_fail(e, "D2H keys");
+    }
+    if (!rc) {
+      std::vector<uint8_t> seen(nn, 0); uint64_t left = nn;
+      const uint64_t mask = (1ull << a->host.rank_bits) - 1;
+      for (uint64_t k : keys) { uint32_t r = (uint32_t)(k & mask); if (!seen[r]) { seen[r] = 1; left--; } }
+      *out_bool = left == 0;
+    }
+  }
+  release_ws(a, ws);
+  return rc;
+}
+
+int am_shard_plan(uint64_t text_len, uint64_t halo_bytes, uint32_t n_shards, uint32_t r, uint64_t* warm_begin, uint64_t* begin, uint64_t* end) {
+  if (n_shards == 0 || r >= n_shards || !warm_begin || !begin || !end) return fail(AM_E_BADARG, "bad shard plan arguments");
+  // contiguous ranges, 16-byte aligned cut points (the kernels read 16-byte granules)
+  auto cut = [&](uint32_t i) -> uint64_t {
+    if (i >= n_shards) return text_len;
+    unsigned __int128 p = (unsigned __int128)text_len * i / n_shards;
+    return (uint64_t)p & ~15ull;
+  };
+  *begin = cut(r); *end = cut(r + 1);
+  *warm_begin = *begin > halo_bytes ? *begin - halo_bytes : 0;
+  return AM_OK;
+}
+
+int am_lower_utf8(const am_lower_table* lower, am_u8slice text, uint8_t* out, size_t cap, uint64_t* out_len) {
+  int rc = check_slice(text); if (rc) return rc;
+  if (!out_len) return fail(AM_E_BADARG, "out_len is null");
+  LowerTable lt;
+  if ((rc = build_lower_table(lower, &lt))) return fail(rc, "bad lower table");
+  std::vector<uint8_t> v;
+  lower_utf8_host(lt, text.ptr + text.off, text.len, &v);
+  *out_len = v.size();
+  if (v.size() > cap) return fail(AM_E_OVERFLOW, "output buffer too small");
+  if (!v.empty()) { if (!out) return fail(AM_E_BADARG, "out is null"); std::memcpy(out, v.data(), v.size()); }
+  return AM_OK;
+}
+
+int am_skip_code_points_backwards(am_u8slice text, int64_t index0, int64_t n0, int64_t* out_index) {
+  // Utf8.hs:256-276
+  int rc = check_slice(text); if (rc) return rc;
+  if (!out_index) return fail(AM_E_BADARG, "out_index is null");
+  if (index0 >= text.len) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
+  const uint8_t* d = text.ptr;
+  int64_t index = index0 + text.off, n = n0;
+  for (;;) {
+    if (index >= 0 && (d[index] & 0xC0) == 0x80) { index--; continue; }
+    if (n == 0) {
+      if (index < 0) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
+      *out_index = index - text.off; return AM_OK;
+    }
+    if (index < 0) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
+    index--; n--;
+  }
+}
+
+void am_free(void* p) { std::free(p); }
+uint64_t am_replacer_last_passes(void) { return g_last_passes; }
+
+// ---- synthetic workloads ----------------------------------------------------------------------------------------------
+int am_synth_fill_dev(void* dev_buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* alphabet, uint32_t alphabet_len, void* stream) {
+  if (usable_device_count() == 0) return fail(AM_E_NODEVICE, "no sm_100 CUDA device");
+  if (!alphabet || alphabet_len == 0 || alphabet_len > 256 || (len && !dev_buf)) return fail(AM_E_BADARG, "bad synth arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* d_alpha = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_alpha, 256);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  e = cudaMemcpyAsync(d_alpha, alphabet, alphabet_len, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_synth_fill(static_cast<uint8_t*>(dev_buf), len, first, seed, d_alpha, alphabet_len, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_alpha);
+  return e == cudaSuccess ? AM_OK : cuda_fail(e, "synth fill");
+}
+
+int am_synth_plant_dev(void* dev_buf, uint64_t len, uint64_t first, uint64_t seed, const am_u8slice* needles, size_t n, uint32_t block, void* stream) {
+  if (usable_device_count() == 0) return fail(AM_E_NODEVICE, "no sm_100 CUDA device");
+  if (!needles || n == 0 || block < 64 || (len && !dev_buf)) return fail(AM_E_BADARG, "bad synth arguments");
+  std::vector<uint8_t> bytes; std::vector<uint32_t> off(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (needles[i].len < 0 || needles[i].len > 16) return fail(AM_E_BADARG, "planted needles must be at most 16 bytes");
+    bytes.insert(bytes.end(), needles[i].ptr + needles[i].off, needles[i].ptr + needles[i].off + needles[i].len);
+    off[i + 1] = (uint32_t)bytes.size();
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* d_b = nullptr; uint32_t* d_o = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_b, bytes.size() + 16);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, off.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_o, off.data(), off.size() * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_synth_plant(static_cast<uint8_t*>(dev_buf), len, first, seed, d_b, d_o, (uint32_t)n, block, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (d_b) cudaFree(d_b);
+  if (d_o) cudaFree(d_o);
+  return e == cudaSuccess ? AM_OK : cuda_fail(e, "synth plant");
+}
+
+}  // extern "C"

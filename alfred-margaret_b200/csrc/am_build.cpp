@@ -1,0 +1,285 @@
+// am_build.cpp -- host-side construction of the byte-level automaton image.
+//
+// Semantics follow `build` in src/Data/Text/AhoCorasick/Automaton.hs:176-200 (trie :249-292,
+// failure links :336-362, merged outputs :367-380); the LAYOUT is this library's own (see
+// am_internal.h).  What must be preserved for bit-exact results:
+//   * a needle given twice is reported twice, the later-inserted one first (:263);
+//   * values[s] = own(s) ++ values[fail s] (:373-376): at one end position, longer needles first;
+//   * the empty needle sits at the root, is inherited by every state and is reported after
+//     every successful transition, never while sitting at the root (:499-503, :517-519).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+#include "am_internal.h"
+
+namespace am {
+
+static int utf8_len(uint32_t c) { return c < 0x80 ? 1 : c < 0x800 ? 2 : c < 0x10000 ? 3 : 4; }
+
+int build_lower_table(const am_lower_table* in, LowerTable* out) {
+  out->stage1.assign(LOWER_STAGE1, 0);
+  out->stage2.assign(128, 0);
+  out->any_length_change = false;
+  if (!in || in->n == 0) return AM_OK;
+  if (!in->pairs) return AM_E_BADARG;
+  std::unordered_map<uint32_t, uint16_t> block_of;  // cp >> 7 -> block id
+  for (size_t i = 0; i < in->n; i++) {
+    uint32_t from = in->pairs[i].from_cp, to = in->pairs[i].to_cp;
+    if (from >= 0x110000 || to >= 0x110000) return AM_E_BADARG;
+    if (from < 128) continue;  // ASCII is lowered by toLowerAscii (Utf8.hs:131-135, :150)
+    uint32_t b = from >> LOWER_BLOCK_SHIFT;
+    auto it = block_of.find(b);
+    uint16_t id;
+    if (it == block_of.end()) {
+      if (out->stage2.size() / 128 >= 0xFFFF) return AM_E_BADARG;
+      id = (uint16_t)(out->stage2.size() / 128);
+      out->stage2.resize(out->stage2.size() + 128, 0);
+      block_of.emplace(b, id);
+      out->stage1[b] = id;
+    } else {
+      id = it->second;
+    }
+    out->stage2[(size_t)id * 128 + (from & 127)] = (int32_t)to - (int32_t)from;
+    if (utf8_len(from) != utf8_len(to)) out->any_length_change = true;
+  }
+  return AM_OK;
+}
+
+namespace {
+
+struct Builder {
+  // temporary trie in insertion order
+  std::vector<uint32_t> parent{0};
+  std::vector<uint8_t> in_byte{0};
+  std::unordered_map<uint64_t, uint32_t> edge;  // state << 8 | byte -> child
+  uint32_t add(uint32_t s, uint8_t b) {
+    uint64_t k = ((uint64_t)s << 8) | b;
+    auto it = edge.find(k);
+    if (it != edge.end()) return it->second;
+    uint32_t c = (uint32_t)parent.size();
+    parent.push_back(s); in_byte.push_back(b);
+    edge.emplace(k, c);
+    return c;
+  }
+};
+
+uint32_t next_pow2(uint64_t x) { uint32_t p = 16; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower,
+                         HostAutomaton* A, std::string* err) {
+  if (n > 0 && !needles) { *err = "needles is null"; return AM_E_BADARG; }
+  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) { *err = "unknown case sensitivity"; return AM_E_BADARG; }
+  if (n >= (1ull << 31)) { *err = "too many needles"; return AM_E_BADARG; }
+  A->case_sensitivity = cs;
+  A->num_needles = (uint32_t)n;
+  int rc = build_lower_table(cs == AM_IGNORE_CASE ? lower : nullptr, &A->lower);
+  if (rc != AM_OK) { *err = "bad lower table"; return rc; }
+
+  // ---- 1. trie over bytes, insertion order ----------------------------------------------------
+  Builder B;
+  B.edge.reserve(n * 8 + 16);
+  std::vector<uint32_t> term(n);
+  std::vector<uint32_t> len_bytes(n), len_cps(n);
+  A->min_len = 0xFFFFFFFFu; A->max_len = 0; A->max_len_cps = 0; A->num_empty = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (needles[i].len < 0 || needles[i].off < 0 || (needles[i].len > 0 && !needles[i].ptr)) { *err = "bad needle slice"; return AM_E_BADARG; }
+    if ((uint64_t)needles[i].len >= (1ull << 24)) { *err = "needle longer than 16 MiB"; return AM_E_BADARG; }
+    const uint8_t* d = needles[i].ptr + needles[i].off;
+    uint32_t len = (uint32_t)needles[i].len, s = 0, cps = 0;
+    for (uint32_t k = 0; k < len; k++) { s = B.add(s, d[k]); cps += (d[k] & 0xC0) != 0x80; }
+    term[i] = s; len_bytes[i] = len; len_cps[i] = cps;
+    if (len == 0) { A->num_empty++; continue; }
+    A->min_len = std::min(A->min_len, len); A->max_len = std::max(A->max_len, len);
+    A->max_len_cps = std::max(A->max_len_cps, cps);
+  }
+  if (A->min_len == 0xFFFFFFFFu) A->min_len = 0;
+  const uint32_t S = (uint32_t)B.parent.size();
+  if (S >= ID_MASK) { *err = "too many states"; return AM_E_BADARG; }
+  A->num_states = S;
+
+  // ---- 2. BFS renumbering (shallow states get small ids; fail(s) < s) -----------------------------
+  std::vector<uint32_t> tmp_child_off(S + 1, 0);
+  for (uint32_t s = 1; s < S; s++) tmp_child_off[B.parent[s] + 1]++;
+  for (uint32_t s = 0; s < S; s++) tmp_child_off[s + 1] += tmp_child_off[s];
+  std::vector<uint32_t> tmp_children(S ? S - 1 : 0);
+  {
+    std::vector<uint32_t> fill(tmp_child_off.begin(), tmp_child_off.end() - 1);
+    for (uint32_t s = 1; s < S; s++) tmp_children[fill[B.parent[s]]++] = s;
+    for (uint32_t s = 0; s < S; s++)
+      std::sort(tmp_children.begin() + tmp_child_off[s], tmp_children.begin() + tmp_child_off[s + 1],
+                [&](uint32_t a, uint32_t b) { return B.in_byte[a] < B.in_byte[b]; });
+  }
+  std::vector<uint32_t> new_id(S), order(S);
+  {
+    uint32_t head = 0, tail = 0;
+    order[tail++] = 0;
+    while (head < tail) {
+      uint32_t s = order[head];
+      new_id[s] = head++;
+      for (uint32_t c = tmp_child_off[s]; c < tmp_child_off[s + 1]; c++) order[tail++] = tmp_children[c];
+    }
+  }
+  A->parent.resize(S); A->in_byte.resize(S); A->depth.resize(S); A->boundary.resize(S);
+  A->child_off.assign(S + 1, 0); A->child_state.resize(S ? S - 1 : 0); A->child_byte.resize(S ? S - 1 : 0);
+  std::vector<uint8_t> rem(S, 0);  // continuation bytes still expected after this state's prefix
+  for (uint32_t k = 0; k < S; k++) {
+    uint32_t old = order[k];
+    A->parent[k] = new_id[B.parent[old]];
+    A->in_byte[k] = B.in_byte[old];
+    if (k == 0) { A->depth[0] = 0; rem[0] = 0; A->boundary[0] = 1; }
+    else {
+      uint32_t p = A->parent[k]; uint8_t b = A->in_byte[k];
+      A->depth[k] = A->depth[p] + 1;
+      if (rem[p] > 0) rem[k] = rem[p] - 1;
+      else rem[k] = b < 0xC0 ? 0 : b < 0xE0 ? 1 : b < 0xF0 ? 2 : 3;  // decodeN's length rule, Utf8.hs:344-350
+      A->boundary[k] = rem[k] == 0;
+    }
+    A->child_off[k + 1] = A->child_off[k] + (tmp_child_off[old + 1] - tmp_child_off[old]);
+  }
+  for (uint32_t k = 0; k < S; k++) {
+    uint32_t old = order[k], o = A->child_off[k];
+    for (uint32_t c = tmp_child_off[old]; c < tmp_child_off[old + 1]; c++, o++) {
+      A->child_state[o] = new_id[tmp_children[c]];
+      A->child_byte[o] = B.in_byte[tmp_children[c]];
+    }
+  }
+  auto goto_child = [&](uint32_t s, uint8_t b) -> uint32_t {
+    const uint8_t* lo = A->child_byte.data() + A->child_off[s];
+    const uint8_t* hi = A->child_byte.data() + A->child_off[s + 1];
+    const uint8_t* it = std::lower_bound(lo, hi, b);
+    if (it != hi && *it == b) return A->child_state[it - A->child_byte.data()];
+    return NONE;
+  };
+
+  // ---- 3. failure links (standard AC; equals buildFallbackMap :336-362) ----------------------------
+  A->fail.assign(S, 0);
+  for (uint32_t s = 1; s < S; s++) {  // BFS order: parent and all shallower states are done
+    uint32_t p = A->parent[s]; uint8_t b = A->in_byte[s];
+    uint32_t f = 0;
+    if (p != 0) {
+      uint32_t st = p;
+      while (st != 0) {
+        uint32_t g = A->fail[st];
+        uint32_t hit = goto_child(g, b);
+        if (hit != NONE) { f = hit; break; }
+        st = g;
+      }
+    }
+    A->fail[s] = f;
+  }
+
+  // ---- 4. needle ranks and output chains ---------------------------------------------------------------
+  // Rank needles by (byte length descending, index descending).  All matches ending at one
+  // position are suffix-nested and distinct, so ascending rank is the reference's order there.
+  A->id_of_rank.resize(n);
+  std::iota(A->id_of_rank.begin(), A->id_of_rank.end(), 0u);
+  std::sort(A->id_of_rank.begin(), A->id_of_rank.end(), [&](uint32_t a, uint32_t b) {
+    if (len_bytes[a] != len_bytes[b]) return len_bytes[a] > len_bytes[b];
+    return a > b;
+  });
+  A->rank_of_id.resize(n); A->len_of_rank.resize(n);
+  for (uint32_t r = 0; r < n; r++) { A->rank_of_id[A->id_of_rank[r]] = r; A->len_of_rank[r] = len_bytes[A->id_of_rank[r]]; }
+  A->rank_bits = 1; while ((1ull << A->rank_bits) < n) A->rank_bits++;
+
+  A->own_off.assign(S + 1, 0);
+  for (size_t i = 0; i < n; i++) A->own_off[new_id[term[i]] + 1]++;
+  for (uint32_t s = 0; s < S; s++) A->own_off[s + 1] += A->own_off[s];
+  A->own_rank.resize(n);
+  {
+    std::vector<uint32_t> fill(A->own_off.begin(), A->own_off.end() - 1);
+    for (uint32_t r = 0; r < n; r++) {  // ascending rank => within a state: index descending (later duplicate first)
+      uint32_t s = new_id[term[A->id_of_rank[r]]];
+      A->own_rank[fill[s]++] = r;
+    }
+  }
+  // chain(s) = own(s) ++ chain(fail s), but only code-point-boundary states report, and the root
+  // itself never reports (its own list -- the empty needles -- is only inherited).
+  A->first_out.assign(S, NONE); A->next_out.assign(S, NONE); A->chain_count.assign(S, 0);
+  const bool root_has_own = A->own_off[1] > A->own_off[0];
+  for (uint32_t s = 1; s < S; s++) {
+    if (!A->boundary[s]) continue;  // mid code point: nothing is reported here
+    uint32_t f = A->fail[s];
+    uint32_t inherited, inherited_count;
+    if (f == 0) { inherited = root_has_own ? 0u : NONE; inherited_count = A->own_off[1] - A->own_off[0]; }
+    else { inherited = A->first_out[f]; inherited_count = A->chain_count[f]; }
+    bool has_own = A->own_off[s + 1] > A->own_off[s];
+    A->next_out[s] = inherited;
+    A->first_out[s] = has_own ? s : inherited;
+    A->chain_count[s] = (A->own_off[s + 1] - A->own_off[s]) + inherited_count;
+  }
+  auto tagged = [&](uint32_t s) -> uint32_t {
+    return s | (A->first_out[s] != NONE ? OUT_FLAG : 0u) | (A->own_off[s + 1] > A->own_off[s] ? OWN_FLAG : 0u);
+  };
+
+  // ---- 5. halo ---------------------------------------------------------------------------------------------
+  // CaseSensitive: a match ending after `begin` starts at most max_len - 1 bytes before it.
+  // IgnoreCase: the walk restarts on a code point boundary at least max_len_cps code points
+  // (<= 4 bytes each) before the first code point it reports, +3 for snapping forward.
+  if (cs == AM_CASE_SENSITIVE) A->halo_bytes = A->max_len > 0 ? A->max_len - 1 : 0;
+  else A->halo_bytes = A->max_len_cps > 0 ? 4ull * A->max_len_cps + 4 : 0;
+
+  // ---- 6. dense rows for the shallowest states ---------------------------------------------------------------
+  {
+    uint32_t cap = 16384;  // 16 MiB of rows at most: stays L2-resident (126 MB L2)
+    A->dense_states = std::min(S, cap);
+    A->dense.assign((size_t)A->dense_states * 256, 0);
+    for (uint32_t s = 0; s < A->dense_states; s++) {
+      uint32_t* row = A->dense.data() + (size_t)s * 256;
+      if (s == 0) { for (int b = 0; b < 256; b++) row[b] = 0; }
+      else std::memcpy(row, A->dense.data() + (size_t)A->fail[s] * 256, 256 * sizeof(uint32_t));  // fail(s) < s
+      for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) row[A->child_byte[c]] = tagged(A->child_state[c]);
+    }
+  }
+
+  // ---- 7. hashed goto edges ----------------------------------------------------------------------------------------
+  {
+    uint32_t cap = next_pow2((uint64_t)(S - 1) * 2 + 16);
+    A->edges.assign(cap, EdgeSlot{NONE, NONE, NONE, 0});
+    A->edge_mask = cap - 1;
+    for (uint32_t s = 0; s < S; s++)
+      for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) {
+        uint32_t b = A->child_byte[c];
+        uint64_t key = ((uint64_t)s << 8) | b;
+        uint32_t i = edge_hash(s, b) & A->edge_mask;
+        while (A->edges[i].child != NONE) i = (i + 1) & A->edge_mask;
+        A->edges[i] = EdgeSlot{(uint32_t)key, (uint32_t)(key >> 32), tagged(A->child_state[c]), 0};
+      }
+  }
+
+  // ---- 8. q-gram filter + jump table (filter kernel; not applicable with empty needles) ------------------------
+  A->q = 0; A->filter_keys = 0;
+  if (A->num_empty == 0 && A->min_len > 0) {
+    A->q = std::min<uint32_t>(4, A->min_len);
+    const uint32_t q = A->q;
+    std::vector<std::pair<uint32_t, uint32_t>> keys;  // (q-gram, state at depth q)
+    for (uint32_t s = 0; s < S; s++) {
+      if (A->depth[s] != q) { if (A->depth[s] > q) break; continue; }
+      uint32_t g = 0, t = s;
+      for (uint32_t k = q; k-- > 0;) { g |= (uint32_t)A->in_byte[t] << (8 * k); t = A->parent[t]; }
+      keys.emplace_back(g, s);
+    }
+    A->filter_keys = (uint32_t)keys.size();
+    A->filter.assign(FILTER_WORDS, 0);
+    A->filter2.assign((1u << FILTER2_LOG2_BITS) / 32, 0);
+    uint32_t cap = next_pow2((uint64_t)keys.size() * 2 + 16);
+    A->jump.assign(cap, JumpSlot{0, NONE});
+    A->jump_mask = cap - 1;
+    for (auto& kv : keys) {
+      uint32_t row, bit;
+      filter_cell(kv.first, &row, &bit);
+      for (int lane = 0; lane < 32; lane++) A->filter[(size_t)row * 32 + lane] |= 1u << bit;
+      uint32_t b2 = filter2_bit(kv.first);
+      A->filter2[b2 >> 5] |= 1u << (b2 & 31);
+      uint32_t i = jump_hash(kv.first) & A->jump_mask;
+      while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
+      A->jump[i] = JumpSlot{kv.first, tagged(kv.second)};
+    }
+  }
+  return AM_OK;
+}
+
+}  // namespace am

@@ -1,0 +1,114 @@
+// am_internal.h -- internal structures of libam_b200 (host build + device image).
+//
+// The reference keys its automaton on code points and scans edge lists linearly
+// (src/Data/Text/AhoCorasick/Automaton.hs:75-123).  This implementation is NOT a port of
+// that layout.  It keys on BYTES (valid UTF-8 needles can only occur at code point boundaries
+// of valid UTF-8 text) and keeps four device structures:
+//
+//   filter   : q-gram membership bitmap (q = min(4, shortest needle) bytes), one private copy
+//              per shared-memory bank (32 x 4 KiB) so a warp's 32 probes never conflict;
+//   jump     : open-addressed table  q-gram -> trie state at depth q;
+//   edges    : open-addressed table  (state, byte) -> child  (the flattened goto function);
+//   dense    : failure-resolved 256-wide rows for the shallowest states + fail links, used by
+//              the per-segment walk kernel (general path: empty needles, huge match density).
+//
+// Output order is reproduced by ranking needles (longer first, later-inserted duplicate
+// first: Automaton.hs:263, :373-376) and sorting (end_pos, rank) keys on the device.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "am_b200.h"
+
+namespace am {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t OUT_FLAG = 0x80000000u;   // stored state id: its output chain (own ++ inherited) is non-empty
+constexpr uint32_t OWN_FLAG = 0x40000000u;   // stored state id: some needle ends exactly at this state
+constexpr uint32_t ID_MASK = 0x3FFFFFFFu;
+
+constexpr int FILTER_ROWS = 1024;            // rows of 32 words (one word per bank) => 128 KiB image
+constexpr int FILTER_WORDS = FILTER_ROWS * 32;
+constexpr uint32_t HASH_MUL = 0x9E3779B1u;   // filter hash multiplier
+constexpr uint32_t HASH_MUL2 = 0x85EBCA6Bu;  // second-level filter / table hash multiplier
+constexpr int FILTER2_LOG2_BITS = 18;        // second-level bitmap: 2^18 bits = 32 KiB (shared memory)
+
+constexpr uint32_t LOWER_BLOCK_SHIFT = 7;    // two-stage lower-case table: 128 code points per block
+constexpr uint32_t LOWER_STAGE1 = 0x110000 >> LOWER_BLOCK_SHIFT;
+
+struct EdgeSlot { uint32_t key_lo, key_hi, child, pad; };   // key = state << 8 | byte ; child carries OUT_FLAG
+struct JumpSlot { uint32_t key, state; };                    // state == NONE => empty ; state carries OUT_FLAG
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x;
+}
+
+// Two-stage table for Char.toLower above ASCII (Utf8.hs:148-151): delta[stage1[cp >> 7] * 128 + (cp & 127)].
+struct LowerTable {
+  std::vector<uint16_t> stage1;   // LOWER_STAGE1 entries; block 0 is the all-zero (identity) block
+  std::vector<int32_t> stage2;    // blocks * 128 deltas
+  bool any_length_change = false; // some pair changes the UTF-8 byte length
+  uint32_t lower(uint32_t cp) const {
+    if (cp < 128) return (cp >= 'A' && cp <= 'Z') ? cp + 0x20 : cp;
+    if (cp >= 0x110000 || stage1.empty()) return cp;
+    return (uint32_t)((int32_t)cp + stage2[(size_t)stage1[cp >> LOWER_BLOCK_SHIFT] * 128 + (cp & 127)]);
+  }
+};
+int build_lower_table(const am_lower_table* in, LowerTable* out);
+
+// Host image of the byte-level automaton; states are numbered in BFS order (root = 0).
+struct HostAutomaton {
+  int case_sensitivity = AM_CASE_SENSITIVE;
+  uint32_t num_needles = 0;
+  uint32_t num_states = 1;
+  uint32_t min_len = 0, max_len = 0;   // bytes, over non-empty needles
+  uint32_t max_len_cps = 0;
+  uint32_t num_empty = 0;              // empty needles (reported after every successful transition, A.4)
+  uint32_t q = 0;                      // filter q-gram length, 0 => filter kernel not applicable
+  uint32_t rank_bits = 1;
+  uint64_t halo_bytes = 0;             // bytes a shard needs before its report range
+
+  std::vector<uint32_t> fail, depth, parent;
+  std::vector<uint8_t> in_byte, boundary;       // boundary: the state's byte prefix ends on a code point boundary
+  std::vector<uint32_t> child_off, child_state; // CSR, children sorted by byte
+  std::vector<uint8_t> child_byte;
+  std::vector<uint32_t> own_off, own_rank;      // CSR: ranks of the needles ending exactly at the state, ascending
+  std::vector<uint32_t> first_out, next_out;    // output chain (NONE = end); see build
+  std::vector<uint32_t> chain_count;            // total matches reported when arriving at the state
+  std::vector<uint32_t> rank_of_id, id_of_rank, len_of_rank;
+
+  uint32_t dense_states = 0;                    // rows in `dense`
+  std::vector<uint32_t> dense;                  // dense_states * 256, failure-resolved, OUT_FLAG tagged
+  std::vector<EdgeSlot> edges; uint32_t edge_mask = 0;
+  std::vector<JumpSlot> jump; uint32_t jump_mask = 0;
+  std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated
+  std::vector<uint32_t> filter2;                // 2^FILTER2_LOG2_BITS bits
+  uint32_t filter_keys = 0;                     // distinct q-grams
+  LowerTable lower;
+};
+
+int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower,
+                         HostAutomaton* out, std::string* err);
+
+inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
+// Filter cell of a (masked) q-gram: row 0..1023 and bit 0..31.  Must match the device code.
+inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
+  uint32_t y = (g * HASH_MUL) >> 15;
+  *row = (y >> 7) & (FILTER_ROWS - 1);
+  *bit = 31u - (y & 31u);   // the kernel rotates left by (y & 31) and tests bit 31
+}
+inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
+// Table hashes (host + device); callers mask with the table's power-of-two mask.
+#if defined(__CUDACC__)
+#define AM_HD __host__ __device__ __forceinline__
+#else
+#define AM_HD inline
+#endif
+AM_HD uint32_t jump_hash(uint32_t g) { uint32_t h = g * HASH_MUL2; return h ^ (h >> 15); }
+AM_HD uint32_t edge_hash(uint32_t state, uint32_t byte) {
+  uint32_t h = state * HASH_MUL + byte * 0x01000193u; return h ^ (h >> 15);
+}
+
+}  // namespace am

@@ -1,0 +1,443 @@
+// am_kernels.cu -- sm_100a scan kernels of libam_b200.
+//
+// Replaces the inner loop of `runWithCase` (src/Data/Text/AhoCorasick/Automaton.hs:442-534):
+// consumeInput / followCodePoint / lookupTransition / collectMatches.  Two formulations:
+//
+//   walk_kernel    every thread walks one text segment (plus a halo of max-needle-length - 1
+//                  bytes of warm-up) through the byte-level goto+failure automaton and reports
+//                  the matches that END inside its segment.  General: handles empty needles,
+//                  IgnoreCase (decode -> Char.toLower table -> re-encode on the fly), any density.
+//
+//   filter_kernel  position-parallel: every text position is tested against a q-gram membership
+//                  bitmap held in shared memory (one private copy per bank => conflict-free),
+//                  staged there by TMA bulk copies; the few surviving positions are compacted
+//                  with warp scans into per-warp queues and verified by walking the failure-less
+//                  goto trie.  The haystack is read once from HBM with 128-bit streaming loads.
+//
+// Both produce (end_pos << rank_bits | rank) keys; sorting them restores the reference's
+// callback order (end_pos ascending, then longest needle / later duplicate first).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "am_device.cuh"
+#include "am_kernels.h"
+
+namespace am {
+
+// =====================================================================================================
+// walk_kernel
+// =====================================================================================================
+constexpr int WALK_THREADS = 128;
+constexpr int WALK_STAGE = 1024;
+
+template <int MODE>
+__device__ __forceinline__ void report_chain(const DevAutomaton& A, const ScanArgs& a, uint32_t tagged,
+                                             uint64_t pos, unsigned long long& local_count,
+                                             KeyStage<WALK_STAGE>* stage) {
+  // collectMatches (Automaton.hs:522-534) over values[state] = own ++ values[fail state]
+  const uint32_t s = tagged & ID_MASK;
+  if (MODE == MODE_COUNT) {
+    local_count += __ldg(A.chain_count + s);
+  } else if (MODE == MODE_ANY) {
+    *a.d_flag = 1;
+  } else {
+    for (uint32_t t = __ldg(A.first_out + s); t != NONE; t = __ldg(A.next_out + t)) {
+      const uint32_t lo = __ldg(A.own_off + t), hi = __ldg(A.own_off + t + 1);
+      for (uint32_t j = lo; j < hi; j++)
+        stage->push(a, ((unsigned long long)(pos + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+    }
+  }
+}
+
+template <bool IGNORE_CASE, int MODE>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs) {
+  __shared__ KeyStage<WALK_STAGE> stage;
+  if (MODE == MODE_EMIT) { stage.init(); __syncthreads(); }
+  unsigned long long local_count = 0;
+
+  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+
+  for (uint64_t seg0 = (uint64_t)blockIdx.x * blockDim.x; seg0 < num_segs; seg0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t seg = seg0 + threadIdx.x;
+    bool live = seg < num_segs;
+    if (MODE == MODE_ANY && live && *reinterpret_cast<volatile int*>(a.d_flag)) live = false;
+    if (live) {
+      // This thread owns the matches whose end position lies in (b, e].
+      const uint64_t b = a.report_begin + seg * seg_bytes;
+      uint64_t e = b + seg_bytes; if (e > a.text_len) e = a.text_len;
+      uint64_t w = b > A.halo ? b - A.halo : 0;  // warm-up start: depth(state) <= max needle length
+      uint32_t state = 0;                        // untagged
+      uint32_t cp = 0, rem = 0;                  // incremental UTF-8 decoder (IgnoreCase)
+      bool synced = !(IGNORE_CASE && (w > 0 || a.report_begin > 0));
+
+      uint64_t v = w + a0; const uint64_t vend = e + a0;
+      while (v < vend) {
+        const uint64_t c = v >> 4;
+        const uint4 q4 = __ldg(base16 + c);
+        const uint32_t words[4] = {q4.x, q4.y, q4.z, q4.w};
+        const uint32_t jlo = (uint32_t)(v & 15);
+        const uint64_t left = vend - (c << 4);
+        const uint32_t jhi = left < 16 ? (uint32_t)left : 16u;
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) {
+          if (j < jlo || j >= jhi) continue;
+          const uint32_t byte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+          const uint64_t pos = (c << 4) + j - a0 + 1;  // offset one past this byte
+          if (!IGNORE_CASE) {
+            const uint32_t t = ac_step(A, state, byte);
+            state = t & ID_MASK;
+            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &stage);
+          } else {
+            // consumeInput (Automaton.hs:468-480): decode one code point (Utf8.hs:337-350), lower it
+            // (Utf8.hs:145-151), feed the bytes of the lowered code point to the byte automaton.
+            if (!synced) { if ((byte & 0xC0u) == 0x80u) continue; synced = true; }  // start on a code point boundary
+            bool complete;
+            if (rem == 0) {
+              if (byte < 0xC0u) { cp = byte; complete = true; }
+              else if (byte < 0xE0u) { cp = byte & 0x1Fu; rem = 1; complete = false; }
+              else if (byte < 0xF0u) { cp = byte & 0x0Fu; rem = 2; complete = false; }
+              else { cp = byte & 0x07u; rem = 3; complete = false; }
+            } else {
+              cp = (cp << 6) | (byte & 0x3Fu); rem--; complete = rem == 0;
+            }
+            if (!complete) continue;
+            const uint32_t l = lower_cp(A, cp);
+            uint32_t t;
+            if (l < 0x80u) { t = ac_step(A, state, l); }
+            else if (l < 0x800u) {
+              t = ac_step(A, state, 0xC0u | (l >> 6));
+              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
+            } else if (l < 0x10000u) {
+              t = ac_step(A, state, 0xE0u | (l >> 12));
+              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
+            } else {
+              t = ac_step(A, state, 0xF0u | (l >> 18));
+              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 12) & 0x3Fu));
+              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
+            }
+            state = t & ID_MASK;
+            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &stage);
+          }
+        }
+        v = (c + 1) << 4;
+      }
+    }
+    if (MODE == MODE_EMIT) stage.flush(a);
+  }
+
+  if (MODE == MODE_COUNT) {
+    // CTA reduction, one global atomic per CTA
+    __shared__ unsigned long long red[WALK_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local_count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long s = 0;
+      for (int i = 0; i < WALK_THREADS / 32; i++) s += red[i];
+      if (s) atomicAdd(a.d_count, s);
+    }
+  }
+}
+
+// =====================================================================================================
+// filter_kernel
+// =====================================================================================================
+constexpr int FK_THREADS = 1024;                 // 32 warps, one CTA per SM (shared memory bound)
+constexpr int FK_WARPS = FK_THREADS / 32;
+constexpr int FK_ITERS = 8;                      // 512-byte warp iterations per warp chunk
+constexpr int FK_CHUNK = FK_ITERS * 512;         // bytes per warp chunk
+constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
+constexpr int FK_QCAP = 256;                     // candidate queue entries per warp
+constexpr int FK_STAGE = 512;                    // staged match keys per CTA
+constexpr int FILTER2_WORDS = (1 << FILTER2_LOG2_BITS) / 32;
+
+struct FilterSmem {
+  uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
+  uint32_t filter2[FILTER2_WORDS];               // 32 KiB
+  uint32_t queue[FK_WARPS][FK_QCAP];             // 32 KiB
+  KeyStage<FK_STAGE> stage;
+  unsigned long long red[FK_WARPS];
+  alignas(8) unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Verify one candidate start position: walk the goto trie (no failure links are needed when every
+// start position is tried) and report every needle that is a prefix of text[i..].
+template <int MODE>
+__device__ __forceinline__ void verify_candidate(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm,
+                                                 const uint32_t* base32, uint64_t nwords, uint32_t a0,
+                                                 uint64_t v, unsigned long long& local_count) {
+  if (v < a0) return;
+  const uint64_t i = v - a0;
+  if (i + A.min_len > a.text_len) return;
+  // exact q-gram at i (two aligned words; the upper one may lie past the last granule)
+  const uint64_t wi = v >> 2;
+  const uint32_t lo = __ldg(base32 + wi);
+  const uint32_t hi = (wi + 1 < nwords) ? __ldg(base32 + wi + 1) : 0u;
+  const uint32_t g = __funnelshift_r(lo, hi, 8u * (uint32_t)(v & 3)) & A.qmask;
+  const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
+  if (!((sm->filter2[b2 >> 5] >> (b2 & 31)) & 1u)) return;
+  uint32_t idx = jump_hash(g) & A.jump_mask;
+  uint32_t st;
+  for (;;) {
+    const uint2 s = __ldg(reinterpret_cast<const uint2*>(A.jump) + idx);
+    if (s.y == NONE) return;
+    if (s.x == g) { st = s.y; break; }
+    idx = (idx + 1) & A.jump_mask;
+  }
+  uint32_t d = A.q;
+  for (;;) {
+    if (st & OWN_FLAG) {
+      const uint64_t end = i + d;
+      if (end > a.report_begin) {
+        const uint32_t s = st & ID_MASK;
+        const uint32_t olo = __ldg(A.own_off + s), ohi = __ldg(A.own_off + s + 1);
+        if (MODE == MODE_COUNT) local_count += ohi - olo;
+        else if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
+        else
+          for (uint32_t j = olo; j < ohi; j++)
+            sm->stage.push(a, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+      }
+    }
+    if (i + d >= a.text_len) return;
+    const uint32_t c = __ldg(a.text + i + d);
+    st = edge_lookup(A, st & ID_MASK, c);
+    if (st == NONE) return;
+    d++;
+  }
+}
+
+template <int MODE, bool Q4>
+__global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FilterSmem* sm = reinterpret_cast<FilterSmem*>(smem_raw);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- stage the filter bitmaps into shared memory with TMA bulk copies -------------------------
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm->mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t total = FILTER_WORDS * 4 + FILTER2_WORDS * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->mbar)), "r"(total) : "memory");
+    constexpr uint32_t CH = 16384;
+    for (uint32_t off = 0; off < FILTER_WORDS * 4; off += CH)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->filter) + off)),
+                   "l"(reinterpret_cast<const unsigned char*>(A.filter) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
+                   : "memory");
+    for (uint32_t off = 0; off < FILTER2_WORDS * 4; off += CH)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->filter2) + off)),
+                   "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
+                   : "memory");
+  }
+  if (MODE == MODE_EMIT) sm->stage.init();
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&sm->mbar)), "r"(0u) : "memory");
+  }
+
+  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  const uint32_t* base32 = reinterpret_cast<const uint32_t*>(base16);
+  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text
+  const uint64_t nwords = nvec * 4;
+  const uint32_t lane_byte = lane << 2;                   // this lane's bank
+  const unsigned char* filt = reinterpret_cast<const unsigned char*>(sm->filter);
+  uint32_t* queue = sm->queue[warp];
+  unsigned long long local_count = 0;
+
+  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
+    const uint64_t tile_v0 = v_begin + tile * FK_TILE;    // virtual (granule-aligned) byte index of the tile
+    const uint64_t chunk_v0 = tile_v0 + (uint64_t)warp * FK_CHUNK;
+    uint32_t qn = 0;                                       // queue fill (warp-uniform)
+
+    uint64_t vec = (chunk_v0 >> 4) + lane;                 // this lane's granule in iteration 0
+    uint4 cur = vec < nvec ? ld_stream_v4(base16 + vec) : make_uint4(0, 0, 0, 0);
+    uint32_t m = 0;                                        // candidate bits, bit (31 - P) <-> position P of the pair
+#pragma unroll 2
+    for (int it = 0; it < FK_ITERS; it++) {
+      // prefetch the next iteration's granule (the last iteration only needs lane 0's first word)
+      uint4 nxt = make_uint4(0, 0, 0, 0);
+      const uint64_t nvi = vec + 32;
+      if (it + 1 < FK_ITERS) { if (nvi < nvec) nxt = ld_stream_v4(base16 + nvi); }
+      else if (lane == 0 && nvi < nvec) nxt.x = __ldg(base32 + nvi * 4);
+      const uint32_t share = lane == 0 ? nxt.x : cur.x;
+      const uint32_t w4 = __shfl_sync(0xFFFFFFFFu, share, (lane + 1) & 31);
+      const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, w4};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
+          if (!Q4) g &= A.qmask;
+          const uint32_t y = (g * HASH_MUL) >> 15;
+          const uint32_t word = *reinterpret_cast<const uint32_t*>(filt + ((y & 0x1FF80u) | lane_byte));
+          const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
+          m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
+        }
+      }
+      if (it & 1) {
+        // ---- compact the candidates of the last two iterations into the warp queue --------------
+        const uint32_t cnt = __popc(m);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total) {
+          const uint32_t pair_off = (uint32_t)(chunk_v0 - tile_v0) + (uint32_t)(it - 1) * 512u + lane * 16u;
+          if (total > FK_QCAP) {
+            // pathological density: every lane verifies its own candidates in place
+            while (m) {
+              const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
+              verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + pair_off + (P >> 4) * 512u + (P & 15u), local_count);
+            }
+          } else {
+            if (qn + total > FK_QCAP) {  // drain first
+              __syncwarp();
+              for (uint32_t k = lane; k < qn; k += 32) verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + queue[k], local_count);
+              __syncwarp();
+              qn = 0;
+            }
+            uint32_t pos = qn + incl - cnt;
+            while (m) {
+              const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
+              queue[pos++] = pair_off + (P >> 4) * 512u + (P & 15u);
+            }
+            qn += total;
+          }
+        }
+        m = 0;
+      }
+      cur = nxt; vec = nvi;
+    }
+    // ---- verify what the chunk left in the queue ---------------------------------------------------
+    __syncwarp();
+    for (uint32_t k = lane; k < qn; k += 32) verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + queue[k], local_count);
+    __syncwarp();
+    if (MODE == MODE_EMIT) sm->stage.flush(a);
+  }
+
+  if (MODE == MODE_COUNT) {
+    for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
+    if (lane == 0) sm->red[warp] = local_count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long s = 0;
+      for (int i = 0; i < FK_WARPS; i++) s += sm->red[i];
+      if (s) atomicAdd(a.d_count, s);
+    }
+  }
+}
+
+// =====================================================================================================
+// key -> am_match
+// =====================================================================================================
+__global__ void unpack_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  am_match mm;
+  mm.end_pos = k >> rank_bits;
+  mm.needle_id = __ldg(id_of_rank + (uint32_t)(k & ((1ull << rank_bits) - 1)));
+  mm.reserved = 0;
+  out[i] = mm;
+}
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <bool IC, int MODE>
+static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
+  if (a.text_len <= a.report_begin) return cudaSuccess;
+  const uint64_t span = a.text_len - a.report_begin;
+  // segment: long enough to amortise the halo, short enough to fill the GPU
+  uint64_t seg = (uint64_t)A.halo * 8; if (seg < 256) seg = 256;
+  const uint64_t want = (uint64_t)sm_count() * 2048;  // threads resident on the whole GPU
+  while (seg > 64 && seg > (uint64_t)A.halo * 2 && (span + seg - 1) / seg < want) seg >>= 1;
+  seg = (seg + 15) & ~15ull;
+  const uint64_t nseg = (span + seg - 1) / seg;
+  uint64_t blocks = (nseg + WALK_THREADS - 1) / WALK_THREADS;
+  const uint64_t max_blocks = (uint64_t)sm_count() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  walk_kernel<IC, MODE><<<(unsigned)blocks, WALK_THREADS, 0, st>>>(A, a, seg, nseg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {
+  if (A.ignore_case) {
+    if (mode == MODE_COUNT) return launch_walk_t<true, MODE_COUNT>(A, a, st);
+    if (mode == MODE_ANY) return launch_walk_t<true, MODE_ANY>(A, a, st);
+    return launch_walk_t<true, MODE_EMIT>(A, a, st);
+  }
+  if (mode == MODE_COUNT) return launch_walk_t<false, MODE_COUNT>(A, a, st);
+  if (mode == MODE_ANY) return launch_walk_t<false, MODE_ANY>(A, a, st);
+  return launch_walk_t<false, MODE_EMIT>(A, a, st);
+}
+
+template <int MODE, bool Q4>
+static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
+  if (a.text_len <= a.report_begin) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
+  // first start position that can produce a match ending after report_begin
+  const uint64_t first = a.report_begin + 1 > A.max_len ? a.report_begin + 1 - A.max_len : 0;
+  const uint64_t v_begin = (first + a0) & ~15ull;
+  const uint64_t v_end = a0 + a.text_len;
+  const uint64_t tiles = (v_end - v_begin + FK_TILE - 1) / FK_TILE;
+  uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
+  filter_kernel<MODE, Q4><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v_begin, tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {
+  const bool q4 = A.q == 4;
+  if (mode == MODE_COUNT) return q4 ? launch_filter_t<MODE_COUNT, true>(A, a, st) : launch_filter_t<MODE_COUNT, false>(A, a, st);
+  if (mode == MODE_ANY) return q4 ? launch_filter_t<MODE_ANY, true>(A, a, st) : launch_filter_t<MODE_ANY, false>(A, a, st);
+  return q4 ? launch_filter_t<MODE_EMIT, true>(A, a, st) : launch_filter_t<MODE_EMIT, false>(A, a, st);
+}
+
+size_t sort_temp_bytes(uint64_t n, int end_bit) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)n, 0, end_bit);
+  return bytes;
+}
+
+cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_t* out, uint64_t n, int end_bit, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortKeys(temp, temp_bytes, in, out, (int64_t)n, 0, end_bit, st);
+}
+
+cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  unpack_kernel<<<blocks, 256, 0, st>>>(keys, n, rank_bits, id_of_rank, out);
+  return cudaGetLastError();
+}
+
+int filter_kernel_smem_bytes() { return (int)sizeof(FilterSmem); }
+
+}  // namespace am

@@ -1,0 +1,131 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/am_b200.h declares, its host-side helpers match the reference's vectors, and compute
+entry points fail loudly (AM_E_NODEVICE) instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "am_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(am_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from alfred_margaret_b200 import _ffi
+    L = _ffi.lib()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), "libam_b200.so does not export %s" % n
+    assert sorted(_ffi.SYMBOLS) == names, "python binding and header disagree"
+    assert L.am_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    from alfred_margaret_b200 import _ffi
+    assert C.sizeof(_ffi.U8Slice) == 24 and C.sizeof(_ffi.Match) == 16 and C.sizeof(_ffi.DevText) == 32
+    assert C.sizeof(_ffi.Options) == 56 and C.sizeof(_ffi.LowerPair) == 8
+
+
+def test_no_cpu_fallback_without_device():
+    from alfred_margaret_b200 import _ffi, automaton
+    if _ffi.lib().am_device_count() > 0:
+        pytest.skip("a device is present")
+    with pytest.raises(_ffi.NoDeviceError):
+        automaton.AcMachine([("abc", 0)])
+    m = automaton.AcMachine([("abc", 0)], device=-2)   # host image only
+    for call in (lambda: m.count_matches("abc"), lambda: m.contains_any("abc"), lambda: m.find_all("abc")):
+        with pytest.raises(_ffi.NoDeviceError):
+            call()
+
+
+def test_host_image_introspection(oracle):
+    from alfred_margaret_b200 import automaton
+    m = automaton.AcMachine([(n, i) for i, n in enumerate(["tshirt", "shirts", "shorts"])], device=-2)
+    info = m.info()
+    assert info == {"num_states": 17, "max_needle_bytes": 6, "halo_bytes": 5, "kernel_kind": 2}
+    # byte-level states == code-point-level states for ASCII; more for multi-byte needles
+    needles = ["groß", "öffnung", "tür", ""]
+    mi = automaton.AcMachine([(n, ()) for n in needles], case_sensitivity=1, device=-2)
+    assert mi.info()["kernel_kind"] == 1                      # IgnoreCase / empty needle -> general walk kernel
+    assert mi.info()["num_states"] == 1 + sum(len(n.encode()) for n in needles)
+    assert oracle.Machine(needles).num_states == 1 + sum(len(n) for n in needles)
+
+
+def test_bad_arguments():
+    from alfred_margaret_b200 import _ffi
+    L = _ffi.lib()
+    h = C.c_void_p()
+    assert L.am_automaton_build(None, 3, 0, None, None, C.byref(h)) == _ffi.AM_E_BADARG
+    assert L.am_automaton_build(None, 0, 7, None, None, C.byref(h)) == _ffi.AM_E_BADARG
+    assert L.am_automaton_build(None, 0, 1, None, None, C.byref(h)) == _ffi.AM_E_BADARG   # IgnoreCase without table
+    assert b"toLower" in L.am_last_error()
+    n = C.c_uint64()
+    assert L.am_count_matches(None, _ffi.U8Slice(0, 0, 0), C.byref(n)) == _ffi.AM_E_BADARG
+
+
+def test_lower_utf8_and_pins(golden, oracle, lower_dense):
+    from alfred_margaret_b200 import utf8
+    for v in golden["lower_code_point"]:
+        assert utf8.lower_code_point(v["from"]) == v["to"], v["note"]
+        assert utf8.lower_utf8(chr(v["from"])) == chr(v["to"]).encode("utf-8")
+    s = "GROẞFRÄSMASCHINENÖFFNUNGSTÜR İK Ⱥ 𝄞💩 ǲ"
+    assert utf8.lower_utf8(s) == oracle.lower_utf8(s, lower_dense)
+    assert utf8.lower_utf8("") == b""
+    rng = np.random.default_rng(1)
+    cps = [int(c) for c in rng.integers(1, 0x11000, size=3000) if not 0xD800 <= c <= 0xDFFF]
+    t = "".join(map(chr, cps))
+    assert utf8.lower_utf8(t) == oracle.lower_utf8(t, lower_dense)
+
+
+def test_skip_code_points_backwards(golden):
+    from alfred_margaret_b200 import utf8
+    for v in golden["skip_code_points_backwards"]:
+        if v["expected"] == "error":
+            with pytest.raises(ValueError):
+                utf8.skip_code_points_backwards(v["text"], v["index"], v["n"])
+        else:
+            assert utf8.skip_code_points_backwards(v["text"], v["index"], v["n"]) == v["expected"], v["src"]
+    # a Text slice with off != 0
+    t = utf8.Text(b"xx" + "aİẞ💩ẞİa".encode("utf-8") + b"yy", 2, 16)
+    assert utf8.skip_code_points_backwards(t, 15, 3) == 6
+
+
+def test_shard_plan():
+    from alfred_margaret_b200 import _ffi
+    L = _ffi.lib()
+    for total in (0, 1, 15, 16, 1000, (1 << 36) + 12345):
+        for n in (1, 2, 4, 8, 7):
+            prev_end = 0
+            for r in range(n):
+                w, b, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
+                assert L.am_shard_plan(total, 15, n, r, C.byref(w), C.byref(b), C.byref(e)) == 0
+                assert b.value == prev_end and e.value >= b.value and w.value == max(0, b.value - 15)
+                assert b.value % 16 == 0
+                prev_end = e.value
+            assert prev_end == total
+    w = C.c_uint64()
+    assert L.am_shard_plan(10, 1, 0, 0, C.byref(w), C.byref(w), C.byref(w)) == _ffi.AM_E_BADARG
+
+
+def test_synth_host_generator():
+    from alfred_margaret_b200 import synth
+    a = synth.fill_host(0, 10000, 43)
+    assert a.size == 10000 and set(a.tolist()) <= set(synth.AZ)
+    assert np.array_equal(synth.fill_host(1234, 777, 43), a[1234:2011])       # pure function of the absolute index
+    counts = np.bincount(a, minlength=128)[97:123]
+    assert counts.min() > 250                                                   # roughly uniform
+    needles = synth.random_needles(50, 42)
+    assert len(set(needles)) == 50 and all(4 <= len(n) <= 16 for n in needles)
+    full = synth.fill_host(0, 40000, 43); synth.plant_host(full, 0, 44, needles)
+    part = synth.fill_host(8000, 9000, 43); synth.plant_host(part, 8000, 44, needles)
+    assert np.array_equal(part, full[8000:17000])                              # shard-consistent planting
+    planted = sum(full.tobytes().count(n) for n in needles)
+    assert planted >= 9
