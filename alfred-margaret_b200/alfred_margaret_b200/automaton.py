@@ -101,18 +101,21 @@ class AcMachine:
             return out[: n.value]
 
     def count_matches(self, text) -> int:
+        t = as_text(text)  # keep the buffer alive across the call
         n = C.c_uint64()
-        _ffi.check(_ffi.lib().am_count_matches(self.handle, as_text(text).slice(), C.byref(n)))
+        _ffi.check(_ffi.lib().am_count_matches(self.handle, t.slice(), C.byref(n)))
         return n.value
 
     def contains_any(self, text) -> bool:
+        t = as_text(text)
         b = C.c_int()
-        _ffi.check(_ffi.lib().am_contains_any(self.handle, as_text(text).slice(), C.byref(b)))
+        _ffi.check(_ffi.lib().am_contains_any(self.handle, t.slice(), C.byref(b)))
         return bool(b.value)
 
     def contains_all(self, text) -> bool:
+        t = as_text(text)
         b = C.c_int()
-        _ffi.check(_ffi.lib().am_contains_all(self.handle, as_text(text).slice(), C.byref(b)))
+        _ffi.check(_ffi.lib().am_contains_all(self.handle, t.slice(), C.byref(b)))
         return bool(b.value)
 
     # ---- device-resident variants (dev_ptr: CUDA device pointer as int) -----------------------------
