@@ -233,7 +233,7 @@ int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_low
   DevAutomaton& D = a->dev;
   std::memset(&D, 0, sizeof D);
   if (H.filter.empty()) { H.filter.assign(FILTER_WORDS, 0); }
-  if (H.filter2.empty()) { H.filter2.assign((1u << FILTER2_LOG2_BITS) / 32, 0); }
+  if (H.filter2.empty()) { H.filter2.assign(T2_WORDS, 0); }
   if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE}); H.jump_mask = 15; }
   if ((rc = upload(a, H.dense, &D.dense)) || (rc = upload(a, H.fail, &D.fail)) || (rc = upload(a, H.edges, &D.edges)) ||
       (rc = upload(a, H.jump, &D.jump)) || (rc = upload(a, H.filter, &D.filter)) || (rc = upload(a, H.filter2, &D.filter2)) ||
@@ -249,6 +249,7 @@ int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_low
   D.q = H.q; D.qmask = qgram_mask(H.q); D.min_len = H.min_len; D.max_len = H.max_len; D.rank_bits = H.rank_bits;
   D.num_states = H.num_states; D.num_needles = H.num_needles;
   D.ignore_case = cs == AM_IGNORE_CASE; D.halo = (uint32_t)H.halo_bytes;
+  D.t2_exact = H.t2_exact; D.t2_empty_key = H.t2_empty_key;
   *out = a;
   return AM_OK;
 }

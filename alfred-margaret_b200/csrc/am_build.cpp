@@ -264,7 +264,6 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     }
     A->filter_keys = (uint32_t)keys.size();
     A->filter.assign(FILTER_WORDS, 0);
-    A->filter2.assign((1u << FILTER2_LOG2_BITS) / 32, 0);
     uint32_t cap = next_pow2((uint64_t)keys.size() * 2 + 16);
     A->jump.assign(cap, JumpSlot{0, NONE});
     A->jump_mask = cap - 1;
@@ -272,11 +271,33 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       uint32_t row, bit;
       filter_cell(kv.first, &row, &bit);
       for (int lane = 0; lane < 32; lane++) A->filter[(size_t)row * 32 + lane] |= 1u << bit;
-      uint32_t b2 = filter2_bit(kv.first);
-      A->filter2[b2 >> 5] |= 1u << (b2 & 31);
       uint32_t i = jump_hash(kv.first) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
       A->jump[i] = JumpSlot{kv.first, tagged(kv.second)};
+    }
+    // second-level table (shared memory, 32 KiB): exact keys when they fit, else a bitmap
+    A->t2_exact = keys.size() <= T2_MAX_EXACT_KEYS;
+    if (A->t2_exact) {
+      std::vector<uint32_t> sorted_keys;
+      for (auto& kv : keys) sorted_keys.push_back(kv.first);
+      std::sort(sorted_keys.begin(), sorted_keys.end());
+      uint32_t empty = 0xFFFFFFFFu;  // any value that is not a key (a text q-gram equal to it is rejected later)
+      while (std::binary_search(sorted_keys.begin(), sorted_keys.end(), empty)) empty--;
+      A->t2_empty_key = empty;
+      A->filter2.assign(T2_WORDS, empty);
+      const uint32_t nb = 1u << T2_LOG2_BUCKETS;
+      for (uint32_t g : sorted_keys) {
+        uint32_t hb = t2_bucket(g);
+        for (;;) {
+          uint32_t* slot = A->filter2.data() + 2 * (size_t)hb;
+          if (slot[0] == empty) { slot[0] = g; break; }
+          if (slot[1] == empty) { slot[1] = g; break; }
+          hb = (hb + 1) & (nb - 1);
+        }
+      }
+    } else {
+      A->filter2.assign(T2_WORDS, 0);
+      for (auto& kv : keys) { uint32_t b2 = filter2_bit(kv.first); A->filter2[b2 >> 5] |= 1u << (b2 & 31); }
     }
   }
   return AM_OK;

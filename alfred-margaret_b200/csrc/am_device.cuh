@@ -31,6 +31,7 @@ struct DevAutomaton {
   uint32_t dense_states, edge_mask, jump_mask;
   uint32_t q, qmask, min_len, max_len, rank_bits, num_states, num_needles;
   uint32_t ignore_case, halo;
+  uint32_t t2_exact, t2_empty_key;
 };
 
 struct ScanArgs {

@@ -33,7 +33,10 @@ constexpr int FILTER_ROWS = 1024;            // rows of 32 words (one word per b
 constexpr int FILTER_WORDS = FILTER_ROWS * 32;
 constexpr uint32_t HASH_MUL = 0x9E3779B1u;   // filter hash multiplier
 constexpr uint32_t HASH_MUL2 = 0x85EBCA6Bu;  // second-level filter / table hash multiplier
-constexpr int FILTER2_LOG2_BITS = 18;        // second-level bitmap: 2^18 bits = 32 KiB (shared memory)
+constexpr int FILTER2_LOG2_BITS = 18;        // second-level table: 32 KiB of shared memory, either a 2^18-bit bitmap ...
+constexpr int T2_WORDS = (1 << FILTER2_LOG2_BITS) / 32;   // ... or 4096 buckets x 2 exact 32-bit q-gram keys
+constexpr int T2_LOG2_BUCKETS = 12;
+constexpr uint32_t T2_MAX_EXACT_KEYS = 4096; // load factor <= 0.5
 
 constexpr uint32_t LOWER_BLOCK_SHIFT = 7;    // two-stage lower-case table: 128 code points per block
 constexpr uint32_t LOWER_STAGE1 = 0x110000 >> LOWER_BLOCK_SHIFT;
@@ -84,7 +87,8 @@ struct HostAutomaton {
   std::vector<EdgeSlot> edges; uint32_t edge_mask = 0;
   std::vector<JumpSlot> jump; uint32_t jump_mask = 0;
   std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated
-  std::vector<uint32_t> filter2;                // 2^FILTER2_LOG2_BITS bits
+  std::vector<uint32_t> filter2;                // T2_WORDS: bitmap, or exact key buckets when t2_exact
+  uint32_t t2_exact = 0, t2_empty_key = 0xFFFFFFFFu;
   uint32_t filter_keys = 0;                     // distinct q-grams
   LowerTable lower;
 };
@@ -100,6 +104,7 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
   *bit = 31u - (y & 31u);   // the kernel rotates left by (y & 31) and tests bit 31
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
+inline uint32_t t2_bucket(uint32_t g) { return (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS); }
 // Table hashes (host + device); callers mask with the table's power-of-two mask.
 #if defined(__CUDACC__)
 #define AM_HD __host__ __device__ __forceinline__

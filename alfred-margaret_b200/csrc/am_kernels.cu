@@ -145,42 +145,76 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(DevAutomaton A, Scan
 // =====================================================================================================
 // filter_kernel
 // =====================================================================================================
+// Per warp, per 4 KiB chunk, in pairs of 512-byte iterations:
+//   1. stream two 16-byte granules per lane from HBM (next pair prefetched into registers) and mirror
+//      them into the warp's 1 KiB shared-memory window;
+//   2. probe the bank-private q-gram bitmap once per text position (32 candidate bits per lane);
+//   3. pop the candidate bits: re-read the exact q-gram from the window, test it against the exact
+//      second-level table T2 (shared memory) -> "survivors" (true q-gram prefix hits, ~0.2 %);
+//   4. survivors are queued per warp and, 32 at a time, walked through the goto trie in HBM/L2
+//      (dense: all lanes busy); matches go to a per-warp stage, flushed with one global atomic.
+// No CTA-wide barrier in the steady state; the only global atomics are per-warp stage flushes.
 constexpr int FK_THREADS = 1024;                 // 32 warps, one CTA per SM (shared memory bound)
 constexpr int FK_WARPS = FK_THREADS / 32;
-constexpr int FK_ITERS = 8;                      // 512-byte warp iterations per warp chunk
-constexpr int FK_CHUNK = FK_ITERS * 512;         // bytes per warp chunk
+constexpr int FK_PAIRS = 4;                      // pairs of 512-byte warp iterations per warp chunk
+constexpr int FK_CHUNK = FK_PAIRS * 1024;        // bytes per warp chunk
 constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
-constexpr int FK_QCAP = 256;                     // candidate queue entries per warp
-constexpr int FK_STAGE = 512;                    // staged match keys per CTA
-constexpr int FILTER2_WORDS = (1 << FILTER2_LOG2_BITS) / 32;
+constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
+constexpr int FK_SQ = 64;                        // survivor queue entries per warp
+constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
+constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
 
 struct FilterSmem {
   uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
-  uint32_t filter2[FILTER2_WORDS];               // 32 KiB
-  uint32_t queue[FK_WARPS][FK_QCAP];             // 32 KiB
-  KeyStage<FK_STAGE> stage;
+  uint32_t t2[T2_WORDS];                         // 32 KiB
+  uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
+  uint2 sq[FK_WARPS][FK_SQ];                     // 16 KiB: (offset from v_begin, q-gram)
+  unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
+  uint32_t sq_n[FK_WARPS];
+  uint32_t wkeys_n[FK_WARPS];
   unsigned long long red[FK_WARPS];
   alignas(8) unsigned long long mbar;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Verify one candidate start position: walk the goto trie (no failure links are needed when every
-// start position is tried) and report every needle that is a prefix of text[i..].
+struct FilterCtx {
+  const uint32_t* base32; uint64_t nwords; uint32_t a0; uint64_t v_begin; uint32_t warp, lane;
+};
+
 template <int MODE>
-__device__ __forceinline__ void verify_candidate(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm,
-                                                 const uint32_t* base32, uint64_t nwords, uint32_t a0,
-                                                 uint64_t v, unsigned long long& local_count) {
-  if (v < a0) return;
-  const uint64_t i = v - a0;
+__device__ __forceinline__ void fk_emit(const ScanArgs& a, FilterSmem* sm, uint32_t warp, unsigned long long key) {
+  const uint32_t i = atomicAdd(&sm->wkeys_n[warp], 1u);
+  if (i < FK_WSTAGE) { sm->wkeys[warp][i] = key; return; }
+  const unsigned long long g = atomicAdd(a.d_count, 1ull);  // stage full: direct append
+  if (g < a.cap) a.d_keys[g] = key;
+}
+
+// Flush the warp's staged keys (call with the warp converged).
+__device__ __forceinline__ void fk_flush(const ScanArgs& a, FilterSmem* sm, uint32_t warp, uint32_t lane, uint32_t min_fill) {
+  __syncwarp();
+  uint32_t n = sm->wkeys_n[warp];
+  if (n > FK_WSTAGE) n = FK_WSTAGE;
+  if (n < min_fill || n == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(a.d_count, (unsigned long long)n);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (lane < n && base + lane < a.cap) a.d_keys[base + lane] = sm->wkeys[warp][lane];
+  __syncwarp();
+  if (lane == 0) sm->wkeys_n[warp] = 0;
+  __syncwarp();
+}
+
+// Walk the goto trie from a survivor (its q-gram is a prefix of some needle, or a rare T2 alias):
+// report every needle that is a prefix of text[i..].  No failure links are needed because every
+// start position is tried (failure-less, position-parallel formulation of Aho-Corasick).
+template <int MODE>
+__device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                               uint32_t v_rel, uint32_t g, unsigned long long& local_count) {
+  const uint64_t v = c.v_begin + v_rel;
+  if (v < c.a0) return;
+  const uint64_t i = v - c.a0;
   if (i + A.min_len > a.text_len) return;
-  // exact q-gram at i (two aligned words; the upper one may lie past the last granule)
-  const uint64_t wi = v >> 2;
-  const uint32_t lo = __ldg(base32 + wi);
-  const uint32_t hi = (wi + 1 < nwords) ? __ldg(base32 + wi + 1) : 0u;
-  const uint32_t g = __funnelshift_r(lo, hi, 8u * (uint32_t)(v & 3)) & A.qmask;
-  const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
-  if (!((sm->filter2[b2 >> 5] >> (b2 & 31)) & 1u)) return;
   uint32_t idx = jump_hash(g) & A.jump_mask;
   uint32_t st;
   for (;;) {
@@ -200,28 +234,66 @@ __device__ __forceinline__ void verify_candidate(const DevAutomaton& A, const Sc
         else if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
         else
           for (uint32_t j = olo; j < ohi; j++)
-            sm->stage.push(a, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+            fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
       }
     }
     if (i + d >= a.text_len) return;
-    const uint32_t c = __ldg(a.text + i + d);
-    st = edge_lookup(A, st & ID_MASK, c);
+    const uint32_t ch = __ldg(a.text + i + d);
+    st = edge_lookup(A, st & ID_MASK, ch);
     if (st == NONE) return;
     d++;
   }
 }
 
-template <int MODE, bool Q4>
+// Drain the warp's survivor queue (warp converged on entry and exit).
+template <int MODE>
+__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                         unsigned long long& local_count, uint32_t min_fill) {
+  __syncwarp();
+  uint32_t n = sm->sq_n[c.warp];
+  if (n > FK_SQ) n = FK_SQ;
+  if (n < min_fill || n == 0) return;
+  for (uint32_t k = c.lane; k < n; k += 32) {
+    const uint2 e = sm->sq[c.warp][k];
+    fk_deep_verify<MODE>(A, a, sm, c, e.x, e.y, local_count);
+  }
+  __syncwarp();
+  if (c.lane == 0) sm->sq_n[c.warp] = 0;
+  __syncwarp();
+  if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
+}
+
+// 16 probes of one granule: w[0..3] own words, w[4] the word that follows.
+template <bool Q4>
+__device__ __forceinline__ uint32_t fk_probe16(const unsigned char* filt, uint32_t lane_byte, uint32_t qmask, uint32_t m,
+                                               uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+  const uint32_t w[5] = {w0, w1, w2, w3, w4};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
+      if (!Q4) g &= qmask;
+      const uint32_t y = (g * HASH_MUL) >> 15;
+      const uint32_t word = *reinterpret_cast<const uint32_t*>(filt + ((y & 0x1FF80u) | lane_byte));
+      const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
+      m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
+    }
+  }
+  return m;
+}
+
+template <int MODE, bool Q4, bool T2X>
 __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FilterSmem* sm = reinterpret_cast<FilterSmem*>(smem_raw);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // ---- stage the filter bitmaps into shared memory with TMA bulk copies -------------------------
+  // ---- stage the filter bitmap and T2 into shared memory with TMA bulk copies -----------------------
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm->mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    constexpr uint32_t total = FILTER_WORDS * 4 + FILTER2_WORDS * 4;
+    constexpr uint32_t total = FILTER_WORDS * 4 + T2_WORDS * 4;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->mbar)), "r"(total) : "memory");
     constexpr uint32_t CH = 16384;
     for (uint32_t off = 0; off < FILTER_WORDS * 4; off += CH)
@@ -229,13 +301,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
                        smem_u32(reinterpret_cast<unsigned char*>(sm->filter) + off)),
                    "l"(reinterpret_cast<const unsigned char*>(A.filter) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
-    for (uint32_t off = 0; off < FILTER2_WORDS * 4; off += CH)
+    for (uint32_t off = 0; off < T2_WORDS * 4; off += CH)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(reinterpret_cast<unsigned char*>(sm->filter2) + off)),
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->t2) + off)),
                    "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
   }
-  if (MODE == MODE_EMIT) sm->stage.init();
+  if (lane == 0) { sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0; }
   __syncthreads();
   {
     uint32_t done = 0;
@@ -245,87 +317,79 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
   }
 
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
-  const uint32_t a0 = (uint32_t)(addr0 & 15);
-  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
-  const uint32_t* base32 = reinterpret_cast<const uint32_t*>(base16);
-  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text
-  const uint64_t nwords = nvec * 4;
+  FilterCtx c;
+  c.a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - c.a0);
+  c.base32 = reinterpret_cast<const uint32_t*>(base16);
+  const uint64_t nvec = (c.a0 + a.text_len + 15) >> 4;    // 16-byte granules overlapping the text
+  c.nwords = nvec * 4; c.v_begin = v_begin; c.warp = warp; c.lane = lane;
   const uint32_t lane_byte = lane << 2;                   // this lane's bank
   const unsigned char* filt = reinterpret_cast<const unsigned char*>(sm->filter);
-  uint32_t* queue = sm->queue[warp];
+  uint32_t* win = sm->window[warp];
+  const uint2* t2b = reinterpret_cast<const uint2*>(sm->t2);
   unsigned long long local_count = 0;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
-    const uint64_t tile_v0 = v_begin + tile * FK_TILE;    // virtual (granule-aligned) byte index of the tile
-    const uint64_t chunk_v0 = tile_v0 + (uint64_t)warp * FK_CHUNK;
-    uint32_t qn = 0;                                       // queue fill (warp-uniform)
-
-    uint64_t vec = (chunk_v0 >> 4) + lane;                 // this lane's granule in iteration 0
-    uint4 cur = vec < nvec ? ld_stream_v4(base16 + vec) : make_uint4(0, 0, 0, 0);
-    uint32_t m = 0;                                        // candidate bits, bit (31 - P) <-> position P of the pair
-#pragma unroll 2
-    for (int it = 0; it < FK_ITERS; it++) {
-      // prefetch the next iteration's granule (the last iteration only needs lane 0's first word)
-      uint4 nxt = make_uint4(0, 0, 0, 0);
-      const uint64_t nvi = vec + 32;
-      if (it + 1 < FK_ITERS) { if (nvi < nvec) nxt = ld_stream_v4(base16 + nvi); }
-      else if (lane == 0 && nvi < nvec) nxt.x = __ldg(base32 + nvi * 4);
-      const uint32_t share = lane == 0 ? nxt.x : cur.x;
-      const uint32_t w4 = __shfl_sync(0xFFFFFFFFu, share, (lane + 1) & 31);
-      const uint32_t w[5] = {cur.x, cur.y, cur.z, cur.w, w4};
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
-          if (!Q4) g &= A.qmask;
-          const uint32_t y = (g * HASH_MUL) >> 15;
-          const uint32_t word = *reinterpret_cast<const uint32_t*>(filt + ((y & 0x1FF80u) | lane_byte));
-          const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
-          m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
-        }
-      }
-      if (it & 1) {
-        // ---- compact the candidates of the last two iterations into the warp queue --------------
-        const uint32_t cnt = __popc(m);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += n; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (total) {
-          const uint32_t pair_off = (uint32_t)(chunk_v0 - tile_v0) + (uint32_t)(it - 1) * 512u + lane * 16u;
-          if (total > FK_QCAP) {
-            // pathological density: every lane verifies its own candidates in place
-            while (m) {
-              const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
-              verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + pair_off + (P >> 4) * 512u + (P & 15u), local_count);
-            }
-          } else {
-            if (qn + total > FK_QCAP) {  // drain first
-              __syncwarp();
-              for (uint32_t k = lane; k < qn; k += 32) verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + queue[k], local_count);
-              __syncwarp();
-              qn = 0;
-            }
-            uint32_t pos = qn + incl - cnt;
-            while (m) {
-              const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
-              queue[pos++] = pair_off + (P >> 4) * 512u + (P & 15u);
-            }
-            qn += total;
+    const uint64_t chunk_v0 = v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK;  // granule-aligned virtual index
+    const uint32_t chunk_rel = (uint32_t)(chunk_v0 - v_begin);
+    uint64_t vec = (chunk_v0 >> 4) + lane;                // this lane's granule of iteration A of the pair
+    uint4 cA = vec < nvec ? ld_stream_v4(base16 + vec) : zero4;
+    uint4 cB = vec + 32 < nvec ? ld_stream_v4(base16 + vec + 32) : zero4;
+#pragma unroll 1
+    for (int pair = 0; pair < FK_PAIRS; pair++) {
+      // prefetch the next pair (after the chunk only lane 0's first word is needed)
+      uint4 nA = zero4, nB = zero4;
+      const uint64_t nv = vec + 64;
+      if (pair + 1 < FK_PAIRS) {
+        if (nv < nvec) nA = ld_stream_v4(base16 + nv);
+        if (nv + 32 < nvec) nB = ld_stream_v4(base16 + nv + 32);
+      } else if (lane == 0 && nv < nvec) nA.x = __ldg(c.base32 + nv * 4);
+      // mirror the pair into the window (exact q-gram recovery for the few candidates)
+      reinterpret_cast<uint4*>(win)[lane] = cA;
+      reinterpret_cast<uint4*>(win)[32 + lane] = cB;
+      if (lane == 0) win[256] = nA.x;
+      const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
+      const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? nA.x : cB.x, (lane + 1) & 31);
+      uint32_t m = 0;                                      // bit (31 - P) <-> position P of the lane's 32
+      m = fk_probe16<Q4>(filt, lane_byte, A.qmask, m, cA.x, cA.y, cA.z, cA.w, w4A);
+      m = fk_probe16<Q4>(filt, lane_byte, A.qmask, m, cB.x, cB.y, cB.z, cB.w, w4B);
+      __syncwarp();
+      // ---- pop candidates, exact second-level test against T2 --------------------------------------
+      while (m) {
+        const uint32_t P = __clz(m);
+        m &= ~(0x80000000u >> P);
+        const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);   // byte offset inside the pair
+        const uint32_t lo = win[o >> 2], hi = win[(o >> 2) + 1];
+        uint32_t g = __funnelshift_r(lo, hi, (o & 3u) * 8u);
+        if (!Q4) g &= A.qmask;
+        bool hit;
+        if (T2X) {
+          uint32_t hb = (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS);
+          for (;;) {
+            const uint2 b = t2b[hb];
+            if (b.x == g || b.y == g) { hit = true; break; }
+            if (b.y == A.t2_empty_key) { hit = false; break; }
+            hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
           }
+        } else {
+          const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
+          hit = (sm->t2[b2 >> 5] >> (b2 & 31)) & 1u;
         }
-        m = 0;
+        if (hit) {
+          const uint32_t v_rel = chunk_rel + (uint32_t)pair * 1024u + o;
+          const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
+          if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(v_rel, g);
+          else fk_deep_verify<MODE>(A, a, sm, c, v_rel, g, local_count);   // queue full: verify in place
+        }
       }
-      cur = nxt; vec = nvi;
+      fk_drain<MODE>(A, a, sm, c, local_count, 32);       // only when a full round of survivors waits
+      cA = nA; cB = nB; vec = nv;
     }
-    // ---- verify what the chunk left in the queue ---------------------------------------------------
-    __syncwarp();
-    for (uint32_t k = lane; k < qn; k += 32) verify_candidate<MODE>(A, a, sm, base32, nwords, a0, tile_v0 + queue[k], local_count);
-    __syncwarp();
-    if (MODE == MODE_EMIT) sm->stage.flush(a);
   }
+  fk_drain<MODE>(A, a, sm, c, local_count, 1);
+  if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
 
   if (MODE == MODE_COUNT) {
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
@@ -394,31 +458,41 @@ cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cuda
   return launch_walk_t<false, MODE_EMIT>(A, a, st);
 }
 
-template <int MODE, bool Q4>
+template <int MODE, bool Q4, bool T2X>
 static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   if (a.text_len <= a.report_begin) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
+    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4, T2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
   // first start position that can produce a match ending after report_begin
   const uint64_t first = a.report_begin + 1 > A.max_len ? a.report_begin + 1 - A.max_len : 0;
-  const uint64_t v_begin = (first + a0) & ~15ull;
   const uint64_t v_end = a0 + a.text_len;
-  const uint64_t tiles = (v_end - v_begin + FK_TILE - 1) / FK_TILE;
-  uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
-  filter_kernel<MODE, Q4><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v_begin, tiles);
-  return cudaGetLastError();
+  for (uint64_t v0 = (first + a0) & ~15ull; v0 < v_end; v0 += FK_SPAN) {
+    const uint64_t span = v_end - v0 < FK_SPAN ? v_end - v0 : FK_SPAN;
+    const uint64_t tiles = (span + FK_TILE - 1) / FK_TILE;
+    const uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
+    filter_kernel<MODE, Q4, T2X><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <int MODE>
+static cudaError_t launch_filter_m(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
+  const bool q4 = A.q == 4, x = A.t2_exact != 0;
+  if (q4) return x ? launch_filter_t<MODE, true, true>(A, a, st) : launch_filter_t<MODE, true, false>(A, a, st);
+  return x ? launch_filter_t<MODE, false, true>(A, a, st) : launch_filter_t<MODE, false, false>(A, a, st);
 }
 
 cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {
-  const bool q4 = A.q == 4;
-  if (mode == MODE_COUNT) return q4 ? launch_filter_t<MODE_COUNT, true>(A, a, st) : launch_filter_t<MODE_COUNT, false>(A, a, st);
-  if (mode == MODE_ANY) return q4 ? launch_filter_t<MODE_ANY, true>(A, a, st) : launch_filter_t<MODE_ANY, false>(A, a, st);
-  return q4 ? launch_filter_t<MODE_EMIT, true>(A, a, st) : launch_filter_t<MODE_EMIT, false>(A, a, st);
+  if (mode == MODE_COUNT) return launch_filter_m<MODE_COUNT>(A, a, st);
+  if (mode == MODE_ANY) return launch_filter_m<MODE_ANY>(A, a, st);
+  return launch_filter_m<MODE_EMIT>(A, a, st);
 }
 
 size_t sort_temp_bytes(uint64_t n, int end_bit) {
