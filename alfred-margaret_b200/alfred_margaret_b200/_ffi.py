@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libam_b200.so")
+LIB_PATH = os.environ.get("AM_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libam_b200.so")  # AM_LIB: kernel-variant builds (development)
 
 AM_OK, AM_E_BADARG, AM_E_OOM, AM_E_CUDA, AM_E_OVERFLOW, AM_E_NODEVICE, AM_E_UNSUPPORTED, AM_E_INTERNAL = range(8)
 _NAMES = ["AM_OK", "AM_E_BADARG", "AM_E_OOM", "AM_E_CUDA", "AM_E_OVERFLOW", "AM_E_NODEVICE", "AM_E_UNSUPPORTED", "AM_E_INTERNAL"]

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -121,6 +122,8 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.d_count = reinterpret_cast<unsigned long long*>(ws->d_scalars);
   sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
   sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
+  static const uint32_t dbg = []() { const char* e = std::getenv("AM_DEBUG_FLAGS"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+  sa.debug = dbg; sa.krow = 4u * FILTER_COPIES;
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);

@@ -270,7 +270,7 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     for (auto& kv : keys) {
       uint32_t row, bit;
       filter_cell(kv.first, &row, &bit);
-      for (int lane = 0; lane < 32; lane++) A->filter[(size_t)row * 32 + lane] |= 1u << bit;
+      for (int c = 0; c < FILTER_COPIES; c++) A->filter[(size_t)row * FILTER_COPIES + c] |= 1u << bit;
       uint32_t i = jump_hash(kv.first) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
       A->jump[i] = JumpSlot{kv.first, tagged(kv.second)};
@@ -284,15 +284,23 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       uint32_t empty = 0xFFFFFFFFu;  // any value that is not a key (a text q-gram equal to it is rejected later)
       while (std::binary_search(sorted_keys.begin(), sorted_keys.end(), empty)) empty--;
       A->t2_empty_key = empty;
+      // buckets of {key0, aux0, key1, aux1}; almost always one probe per lookup: a bucket that would take a
+      // third key is flagged "overflow" and only then does a lookup continue in the next bucket
       A->filter2.assign(T2_WORDS, empty);
-      const uint32_t nb = 1u << T2_LOG2_BUCKETS;
-      for (uint32_t g : sorted_keys) {
+      for (uint32_t bkt = 0; bkt < (1u << T2_LOG2_BUCKETS); bkt++) { A->filter2[4 * (size_t)bkt + 1] = T2_AUX_ANY; A->filter2[4 * (size_t)bkt + 3] = T2_AUX_ANY; }
+      for (auto& kv : keys) {
+        const uint32_t g = kv.first, s = kv.second;
+        // aux: the byte that must follow the q-gram, when every needle through this state continues with it
+        uint32_t aux = T2_AUX_ANY;
+        const bool has_own = A->own_off[s + 1] > A->own_off[s];
+        if (!has_own && A->child_off[s + 1] - A->child_off[s] == 1) aux = A->child_byte[A->child_off[s]];
         uint32_t hb = t2_bucket(g);
         for (;;) {
-          uint32_t* slot = A->filter2.data() + 2 * (size_t)hb;
-          if (slot[0] == empty) { slot[0] = g; break; }
-          if (slot[1] == empty) { slot[1] = g; break; }
-          hb = (hb + 1) & (nb - 1);
+          uint32_t* slot = A->filter2.data() + 4 * (size_t)hb;
+          if (slot[0] == empty) { slot[0] = g; slot[1] = aux; break; }
+          if (slot[2] == empty) { slot[2] = g; slot[3] = (slot[3] & T2_AUX_OVERFLOW) | aux; break; }
+          slot[3] |= T2_AUX_OVERFLOW;   // full: lookups that miss here go on to the next bucket
+          hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
         }
       }
     } else {

@@ -43,6 +43,8 @@ struct ScanArgs {
   uint64_t* d_keys;             // EMIT: (pos << rank_bits | rank)
   uint64_t cap;
   int* d_flag;                  // ANY
+  uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
+  uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)
 };
 
 // ---- small device helpers ------------------------------------------------------------------------

@@ -34,9 +34,11 @@ constexpr int FILTER_WORDS = FILTER_ROWS * 32;
 constexpr uint32_t HASH_MUL = 0x9E3779B1u;   // filter hash multiplier
 constexpr uint32_t HASH_MUL2 = 0x85EBCA6Bu;  // second-level filter / table hash multiplier
 constexpr int FILTER2_LOG2_BITS = 18;        // second-level table: 32 KiB of shared memory, either a 2^18-bit bitmap ...
-constexpr int T2_WORDS = (1 << FILTER2_LOG2_BITS) / 32;   // ... or 4096 buckets x 2 exact 32-bit q-gram keys
-constexpr int T2_LOG2_BUCKETS = 12;
-constexpr uint32_t T2_MAX_EXACT_KEYS = 4096; // load factor <= 0.5
+constexpr int T2_WORDS = (1 << FILTER2_LOG2_BITS) / 32;   // ... or 2048 buckets x 2 x (exact q-gram key, aux)
+constexpr int T2_LOG2_BUCKETS = 11;
+constexpr uint32_t T2_MAX_EXACT_KEYS = 2048; // load factor <= 0.5
+constexpr uint32_t T2_AUX_ANY = 0x100u;      // aux: no constraint on the byte after the q-gram; else that byte's value
+constexpr uint32_t T2_AUX_OVERFLOW = 0x200u; // on slot 1's aux: the bucket overflowed at build time => the lookup continues in the next bucket
 
 constexpr uint32_t LOWER_BLOCK_SHIFT = 7;    // two-stage lower-case table: 128 code points per block
 constexpr uint32_t LOWER_STAGE1 = 0x110000 >> LOWER_BLOCK_SHIFT;
@@ -97,11 +99,28 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
                          HostAutomaton* out, std::string* err);
 
 inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
-// Filter cell of a (masked) q-gram: row 0..1023 and bit 0..31.  Must match the device code.
+// Build-time variants of the filter kernel (A/B-tested on the GPU):
+//   FK_COPIES  private copies of the q-gram bitmap: 32 (32 Ki bits each, conflict-free), 16 (64 Ki bits,
+//              2-way bank conflicts) or 8 (128 Ki bits, ~2.7-way).  Fewer copies = fewer false positives.
+//   FK_WB      "weak bit index": take the bit index from the low 5 bits of the multiplicative hash and
+//              form the address with IMAD (FMA pipe) -- one ALU-pipe instruction less per probe, at the
+//              price of a bit index that only depends on the q-gram's first byte.
+#ifndef FK_COPIES
+#define FK_COPIES 16
+#endif
+#ifndef FK_WB
+#define FK_WB 1
+#endif
+constexpr int FILTER_COPIES = FK_COPIES;
+constexpr int FILTER_ROWBITS = FK_COPIES == 32 ? 10 : FK_COPIES == 16 ? 11 : 12;
+constexpr int FILTER_ROWS_EFF = 1 << FILTER_ROWBITS;
+static_assert(FILTER_ROWS_EFF * FILTER_COPIES == FILTER_WORDS, "filter geometry");
+// Filter cell of a (masked) q-gram: row and bit 0..31.  Must match the device code.
 inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
-  uint32_t y = (g * HASH_MUL) >> 15;
-  *row = (y >> 7) & (FILTER_ROWS - 1);
-  *bit = 31u - (y & 31u);   // the kernel rotates left by (y & 31) and tests bit 31
+  const uint32_t x = g * HASH_MUL;
+  *row = x >> (32 - FILTER_ROWBITS);
+  const uint32_t s = FK_WB ? (x & 31u) : ((x >> 15) & 31u);
+  *bit = 31u - s;   // the kernel rotates left by s and tests bit 31
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
 inline uint32_t t2_bucket(uint32_t g) { return (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS); }

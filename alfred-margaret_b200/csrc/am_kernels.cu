@@ -163,6 +163,18 @@ constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail wo
 constexpr int FK_SQ = 64;                        // survivor queue entries per warp
 constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
 constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
+// Build-time variants (A/B-tested on the GPU):
+//   FK_POP_DENSE  compact candidates with a warp scan and test them 32 at a time, instead of each lane
+//                 popping and testing its own candidates
+#ifndef FK_POP_DENSE
+#define FK_POP_DENSE 0
+#endif
+//   FK_PF         distance (in CTA tiles) of the bulk L2 prefetch issued ahead of the streaming loads; the
+//                 register double-buffer alone keeps too few bytes in flight to cover HBM latency
+#ifndef FK_PF
+#define FK_PF 2
+#endif
+constexpr int FK_CQ = 128;                       // dense pop: candidate queue entries per warp
 
 struct FilterSmem {
   uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
@@ -170,6 +182,10 @@ struct FilterSmem {
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
   uint2 sq[FK_WARPS][FK_SQ];                     // 16 KiB: (offset from v_begin, q-gram)
   unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
+#if FK_POP_DENSE
+  uint16_t cq[FK_WARPS][FK_CQ];                  // 8 KiB: candidate offsets inside the pair
+  uint32_t cq_n[FK_WARPS];
+#endif
   uint32_t sq_n[FK_WARPS];
   uint32_t wkeys_n[FK_WARPS];
   unsigned long long red[FK_WARPS];
@@ -263,9 +279,15 @@ __device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& 
   if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
 }
 
-// 16 probes of one granule: w[0..3] own words, w[4] the word that follows.
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v;
+}
+
+// 16 probes of one granule: w[0..3] own words, w[4] the word that follows.  `filt_lane` is the shared
+// address of this lane's private copy of the bitmap.
 template <bool Q4>
-__device__ __forceinline__ uint32_t fk_probe16(const unsigned char* filt, uint32_t lane_byte, uint32_t qmask, uint32_t m,
+__device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmask, uint32_t krow, uint32_t m,
                                                uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
 #pragma unroll
@@ -274,13 +296,50 @@ __device__ __forceinline__ uint32_t fk_probe16(const unsigned char* filt, uint32
     for (int j = 0; j < 4; j++) {
       uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
       if (!Q4) g &= qmask;
-      const uint32_t y = (g * HASH_MUL) >> 15;
-      const uint32_t word = *reinterpret_cast<const uint32_t*>(filt + ((y & 0x1FF80u) | lane_byte));
+#if FK_WB
+      const uint32_t y = g * HASH_MUL;                     // bit index = low 5 bits, row = top bits
+      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);   // SHF + IMAD(UR) + LDS
+#else
+      const uint32_t y = (g * HASH_MUL) >> 15;             // bits 0..4 bit index, top FILTER_ROWBITS bits row
+      const uint32_t word = lds32((y & (((1u << FILTER_ROWBITS) - 1u) << (17 - FILTER_ROWBITS))) + filt_lane);
+#endif
       const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
       m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
     }
   }
   return m;
+}
+
+// Second-level test of one candidate at byte offset `o` of the warp's window: recover the exact q-gram,
+// look it up in T2 (exact keys + the byte that must follow, or a bitmap for large needle sets).
+// win_s / t2_s: shared-space addresses of the warp's window and of T2.
+template <bool Q4, bool T2X>
+__device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s, uint32_t t2_s, uint32_t o, uint32_t* g_out) {
+  const uint32_t wa = win_s + (o & ~3u);
+  const uint32_t lo = lds32(wa), hi = lds32(wa + 4);
+  const uint32_t sh = (o & 3u) * 8u;
+  uint32_t g = __funnelshift_r(lo, hi, sh);
+  if (!Q4) g &= A.qmask;
+  *g_out = g;
+  if (T2X) {
+    uint32_t hb = (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS);
+    uint32_t aux;
+    for (;;) {
+      const uint4 b = lds128(t2_s + (hb << 4));
+      if (b.x == g) { aux = b.y; break; }
+      if (b.z == g) { aux = b.w; break; }
+      if (!(b.w & T2_AUX_OVERFLOW)) return false;          // the common exit: one probe
+      hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
+    }
+    if (aux & T2_AUX_ANY) return true;
+    uint32_t nb;                                           // text byte right after the q-gram
+    if (Q4) nb = (hi >> sh) & 0xFFu;
+    else nb = (uint32_t)((((unsigned long long)hi << 32) | lo) >> (sh + 8u * A.q)) & 0xFFu;
+    return nb == (aux & 0xFFu);
+  } else {
+    const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
+    return (lds32(t2_s + ((b2 >> 5) << 2)) >> (b2 & 31)) & 1u;
+  }
 }
 
 template <int MODE, bool Q4, bool T2X>
@@ -307,7 +366,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
                    "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
   }
-  if (lane == 0) { sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0; }
+  if (lane == 0) {
+    sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0;
+#if FK_POP_DENSE
+    sm->cq_n[warp] = 0;
+#endif
+  }
   __syncthreads();
   {
     uint32_t done = 0;
@@ -323,10 +387,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
   c.base32 = reinterpret_cast<const uint32_t*>(base16);
   const uint64_t nvec = (c.a0 + a.text_len + 15) >> 4;    // 16-byte granules overlapping the text
   c.nwords = nvec * 4; c.v_begin = v_begin; c.warp = warp; c.lane = lane;
-  const uint32_t lane_byte = lane << 2;                   // this lane's bank
-  const unsigned char* filt = reinterpret_cast<const unsigned char*>(sm->filter);
+  const uint32_t filt_lane = smem_u32(sm->filter) + ((lane & (FK_COPIES - 1u)) << 2);   // this lane's private copy (bank)
   uint32_t* win = sm->window[warp];
-  const uint2* t2b = reinterpret_cast<const uint2*>(sm->t2);
+  const uint32_t win_s = smem_u32(win), t2_s = smem_u32(sm->t2);
   unsigned long long local_count = 0;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
@@ -334,6 +397,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
     const uint64_t chunk_v0 = v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK;  // granule-aligned virtual index
     const uint32_t chunk_rel = (uint32_t)(chunk_v0 - v_begin);
+#if FK_PF > 0
+    if (lane == 0) {   // pull this warp's chunk of a later tile into L2 (one TMA-style bulk prefetch, no registers)
+      const uint64_t pv = (chunk_v0 + (uint64_t)FK_PF * gridDim.x * FK_TILE) >> 4;
+      if (tile + (uint64_t)FK_PF * gridDim.x < num_tiles && pv + FK_CHUNK / 16 <= nvec)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base16 + pv), "r"((uint32_t)FK_CHUNK) : "memory");
+    }
+#endif
     uint64_t vec = (chunk_v0 >> 4) + lane;                // this lane's granule of iteration A of the pair
     uint4 cA = vec < nvec ? ld_stream_v4(base16 + vec) : zero4;
     uint4 cB = vec + 32 < nvec ? ld_stream_v4(base16 + vec + 32) : zero4;
@@ -353,37 +423,76 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
       const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
       const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? nA.x : cB.x, (lane + 1) & 31);
       uint32_t m = 0;                                      // bit (31 - P) <-> position P of the lane's 32
-      m = fk_probe16<Q4>(filt, lane_byte, A.qmask, m, cA.x, cA.y, cA.z, cA.w, w4A);
-      m = fk_probe16<Q4>(filt, lane_byte, A.qmask, m, cB.x, cB.y, cB.z, cB.w, w4B);
+      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
+      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
       __syncwarp();
-      // ---- pop candidates, exact second-level test against T2 --------------------------------------
+      if (a.debug & 1u) { local_count += __popc(m); m = 0; }
+      const uint32_t pair_rel = chunk_rel + (uint32_t)pair * 1024u;
+#if FK_POP_DENSE
+      {
+        // ---- compact the candidate offsets with a warp scan, then test them 32 at a time ----------------
+        const uint32_t cnt = __popc(m);
+#if FK_POP_DENSE == 2
+        // slot allocation with one shared-memory atomic per lane that has candidates
+        uint32_t incl = cnt;
+        if (cnt) incl += atomicAdd(&sm->cq_n[warp], cnt);
+        __syncwarp();
+        const uint32_t total = sm->cq_n[warp];
+        __syncwarp();
+        if (lane == 0) sm->cq_n[warp] = 0;
+#else
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += n; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#endif
+        if (total > FK_CQ) {
+          // pathological density: every lane tests its own candidates
+          while (m) {
+            const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
+            const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);
+            uint32_t g;
+            if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
+              const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
+              if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
+              else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);
+            }
+          }
+        } else if (total) {
+          uint16_t* cq = sm->cq[warp];
+          uint32_t pos = incl - cnt;
+          while (m) {
+            const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
+            cq[pos++] = (uint16_t)(((P & 16u) << 5) | (lane << 4) | (P & 15u));
+          }
+          __syncwarp();
+          for (uint32_t k = lane; k < total; k += 32) {
+            const uint32_t o = cq[k];
+            uint32_t g;
+            if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
+              if (a.debug & 2u) { local_count++; continue; }
+              const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
+              if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
+              else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);
+            }
+          }
+        }
+      }
+#else
+      // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
       while (m) {
         const uint32_t P = __clz(m);
         m &= ~(0x80000000u >> P);
         const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);   // byte offset inside the pair
-        const uint32_t lo = win[o >> 2], hi = win[(o >> 2) + 1];
-        uint32_t g = __funnelshift_r(lo, hi, (o & 3u) * 8u);
-        if (!Q4) g &= A.qmask;
-        bool hit;
-        if (T2X) {
-          uint32_t hb = (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS);
-          for (;;) {
-            const uint2 b = t2b[hb];
-            if (b.x == g || b.y == g) { hit = true; break; }
-            if (b.y == A.t2_empty_key) { hit = false; break; }
-            hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
-          }
-        } else {
-          const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
-          hit = (sm->t2[b2 >> 5] >> (b2 & 31)) & 1u;
-        }
-        if (hit) {
-          const uint32_t v_rel = chunk_rel + (uint32_t)pair * 1024u + o;
+        uint32_t g;
+        if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
+          if (a.debug & 2u) { local_count++; continue; }
           const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-          if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(v_rel, g);
-          else fk_deep_verify<MODE>(A, a, sm, c, v_rel, g, local_count);   // queue full: verify in place
+          if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
+          else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);   // queue full: verify in place
         }
       }
+#endif
       fk_drain<MODE>(A, a, sm, c, local_count, 32);       // only when a full round of survivors waits
       cA = nA; cB = nB; vec = nv;
     }
