@@ -73,6 +73,9 @@ SYMBOLS = {
     "am_free": (None, [C.c_void_p]),
     "am_lower_utf8": (C.c_int, [C.POINTER(LowerTable), U8Slice, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "am_skip_code_points_backwards": (C.c_int, [U8Slice, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "am_profile_enable": (C.c_int, [C.c_int]),
+    "am_profile_last_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "am_profile_kernel_launches": (C.c_uint64, []),
     "am_synth_fill_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint32, C.c_void_p]),
     "am_synth_plant_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(U8Slice), C.c_size_t, C.c_uint32, C.c_void_p]),
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,10 @@ namespace am {
 
 thread_local std::string g_last_error;
 thread_local uint64_t g_last_passes = 0;
+std::atomic<uint64_t> g_kernel_launches{0};
+static std::atomic<int> g_profile{0};
+thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+thread_local bool g_ev_valid = false;
 
 int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -126,7 +131,13 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.debug = dbg; sa.krow = 4u * FILTER_COPIES;
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+  if (prof) {
+    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    cudaEventRecord(g_ev0, st);
+  }
   e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
+  if (prof) { cudaEventRecord(g_ev1, st); g_ev_valid = true; }
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return AM_OK;
 }
@@ -466,6 +477,16 @@ int am_skip_code_points_backwards(am_u8slice text, int64_t index0, int64_t n0, i
 }
 
 void am_free(void* p) { std::free(p); }
+
+int am_profile_enable(int on) { g_profile.store(on ? 1 : 0); return AM_OK; }
+int am_profile_last_scan_ms(float* ms) {
+  if (!ms) return fail(AM_E_BADARG, "ms is null");
+  if (!g_ev_valid) return fail(AM_E_BADARG, "no profiled scan on this thread");
+  cudaError_t e = cudaEventSynchronize(g_ev1);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(ms, g_ev0, g_ev1);
+  return e == cudaSuccess ? AM_OK : cuda_fail(e, "event timing");
+}
+uint64_t am_profile_kernel_launches(void) { return g_kernel_launches.load(); }
 uint64_t am_replacer_last_passes(void) { return g_last_passes; }
 
 // ---- synthetic workloads ----------------------------------------------------------------------------------------------

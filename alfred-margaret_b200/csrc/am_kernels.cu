@@ -552,6 +552,7 @@ static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaS
   uint64_t blocks = (nseg + WALK_THREADS - 1) / WALK_THREADS;
   const uint64_t max_blocks = (uint64_t)sm_count() * 16;
   if (blocks > max_blocks) blocks = max_blocks;
+  g_kernel_launches++;
   walk_kernel<IC, MODE><<<(unsigned)blocks, WALK_THREADS, 0, st>>>(A, a, seg, nseg);
   return cudaGetLastError();
 }
@@ -584,6 +585,7 @@ static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cud
     const uint64_t span = v_end - v0 < FK_SPAN ? v_end - v0 : FK_SPAN;
     const uint64_t tiles = (span + FK_TILE - 1) / FK_TILE;
     const uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
+    g_kernel_launches++;
     filter_kernel<MODE, Q4, T2X><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -617,6 +619,7 @@ cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_
 cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256);
+  g_kernel_launches++;
   unpack_kernel<<<blocks, 256, 0, st>>>(keys, n, rank_bits, id_of_rank, out);
   return cudaGetLastError();
 }

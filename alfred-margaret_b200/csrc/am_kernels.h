@@ -5,7 +5,11 @@
 
 #include "am_device.cuh"
 
+#include <atomic>
+
 namespace am {
+
+extern std::atomic<uint64_t> g_kernel_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
 // Per-segment goto+failure walk (general path).  mode: ScanMode.
 cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);

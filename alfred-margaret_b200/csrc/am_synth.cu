@@ -67,6 +67,7 @@ __global__ void synth_plant_kernel(uint8_t* buf, uint64_t len, uint64_t first, u
 
 cudaError_t launch_synth_fill(uint8_t* buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* d_alpha, uint32_t alpha_len, cudaStream_t st) {
   if (len == 0) return cudaSuccess;
+  g_kernel_launches++;
   synth_fill_kernel<<<148 * 8, 256, 0, st>>>(buf, len, first, seed, d_alpha, alpha_len);
   return cudaGetLastError();
 }
@@ -74,6 +75,7 @@ cudaError_t launch_synth_fill(uint8_t* buf, uint64_t len, uint64_t first, uint64
 cudaError_t launch_synth_plant(uint8_t* buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* d_needle_bytes,
                                const uint32_t* d_needle_off, uint32_t n, uint32_t block, cudaStream_t st) {
   if (len == 0 || n == 0) return cudaSuccess;
+  g_kernel_launches++;
   synth_plant_kernel<<<148 * 4, 256, 0, st>>>(buf, len, first, seed, d_needle_bytes, d_needle_off, n, block);
   return cudaGetLastError();
 }

@@ -158,6 +158,15 @@ int am_lower_utf8(const am_lower_table *lower, am_u8slice text, uint8_t *out, si
 /* Utf8.skipCodePointsBackwards (:256-276); AM_E_BADARG where the reference calls `error`. */
 int am_skip_code_points_backwards(am_u8slice text, int64_t index, int64_t n, int64_t *out_index);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------
+ * am_profile_enable(1) makes every scan record CUDA events around its scan kernel(s) on the stream they
+ * are launched on; am_profile_last_scan_ms returns the device time of the most recent scan on this
+ * thread (kernel only: no sort, no copies).  am_profile_kernel_launches counts every kernel this
+ * library has launched in the process (its own kernels, not the CUB sort's). */
+int am_profile_enable(int on);
+int am_profile_last_scan_ms(float *ms);
+uint64_t am_profile_kernel_launches(void);
+
 /* ---- synthetic workload generator (bench / test tooling; BASELINE.json configs) ----------------
  * Counter-based: byte i depends only on (seed, i), so host and device produce identical text. */
 int am_synth_fill_dev(void *dev_buf, uint64_t len, uint64_t first_byte_index, uint64_t seed,

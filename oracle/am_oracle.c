@@ -370,6 +370,55 @@ uint64_t amo_count_parallel(const amo_machine *m, int cs, const uint32_t *lower,
   return total;
 }
 
+typedef struct { const amo_machine *m; int cs; const uint32_t *lower; amo_u8slice text; int r, threads; int64_t halo; amo_match *buf; int64_t n, cap; } fa_job;
+
+static void *fa_main(void *arg) {
+  fa_job *j = arg;
+  amo_u8slice text = j->text;
+  const uint8_t *base = text.ptr + text.off;
+  int64_t b = text.len * j->r / j->threads, e = text.len * (j->r + 1) / j->threads;
+  while (b > 0 && b < text.len && (base[b] & 0xc0) == 0x80) b++;
+  while (e < text.len && (base[e] & 0xc0) == 0x80) e++;
+  j->n = 0;
+  if (b >= e) return NULL;
+  int64_t w = b - j->halo; if (w < 0) w = 0;
+  while (w > 0 && (base[w] & 0xc0) == 0x80) w--;
+  amo_u8slice shard = { text.ptr, text.off + w, e - w };
+  for (;;) {
+    int64_t n = amo_find_all(j->m, j->cs, j->lower, shard, j->buf, j->cap);
+    if (n <= j->cap) { j->n = n; break; }
+    free(j->buf); j->cap = n + n / 8 + 16; j->buf = malloc(sizeof(amo_match) * (size_t)j->cap);
+  }
+  /* keep the matches ending inside (b, e], rebased to the whole text */
+  int64_t k = 0;
+  for (int64_t i = 0; i < j->n; i++) {
+    int64_t pos = j->buf[i].pos + w;
+    if (pos > b) { j->buf[k].pos = pos; j->buf[k].value = j->buf[i].value; k++; }
+  }
+  j->n = k;
+  return NULL;
+}
+
+int64_t amo_find_all_parallel(const amo_machine *m, int cs, const uint32_t *lower, amo_u8slice text,
+                              amo_match *out, int64_t cap, int threads) {
+  if (threads <= 1 || text.len < (int64_t)threads * 4096) return amo_find_all(m, cs, lower, text, out, cap);
+  if (threads > 256) threads = 256;
+  int64_t halo = cs == AMO_IGNORE_CASE ? 4 * m->max_needle_cps : m->max_needle_bytes;
+  fa_job jobs[256]; pthread_t tids[256];
+  for (int r = 0; r < threads; r++) {
+    int64_t c0 = text.len / threads / 256 + 1024;
+    fa_job j = { m, cs, lower, text, r, threads, halo, malloc(sizeof(amo_match) * (size_t)c0), 0, c0 }; jobs[r] = j;
+    pthread_create(&tids[r], NULL, fa_main, &jobs[r]);
+  }
+  int64_t total = 0;
+  for (int r = 0; r < threads; r++) {
+    pthread_join(tids[r], NULL);
+    for (int64_t i = 0; i < jobs[r].n; i++) { if (total < cap) out[total] = jobs[r].buf[i]; total++; }
+    free(jobs[r].buf);
+  }
+  return total;
+}
+
 /* ---- Replacer, Replacer.hs ---------------------------------------------------------------- */
 struct amo_replacer {
   amo_machine *machine;

@@ -88,6 +88,11 @@ int amo_contains_all(const amo_machine *m, int64_t num_needles, int cs, const ui
 uint64_t amo_count_parallel(const amo_machine *m, int cs, const uint32_t *lower, amo_u8slice text,
                             int threads);
 
+/* Same sharding for the all-matches fold (matches of shard r precede those of shard r + 1, so the
+ * concatenation is in callback order). */
+int64_t amo_find_all_parallel(const amo_machine *m, int cs, const uint32_t *lower, amo_u8slice text,
+                              amo_match *out, int64_t cap, int threads);
+
 /* Replacer, src/Data/Text/AhoCorasick/Replacer.hs:97-116 (build), :200-274 (run). */
 typedef struct amo_replacer amo_replacer;
 /* needles[i] must already be lowered for IgnoreCase (Replacer.hs:105-107, use amo_lower_utf8);

@@ -58,6 +58,7 @@ def lib():
         L.amo_contains_any.argtypes = [C.c_void_p, C.c_int, C.c_void_p, U8Slice]; L.amo_contains_any.restype = C.c_int
         L.amo_contains_all.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, U8Slice]; L.amo_contains_all.restype = C.c_int
         L.amo_find_all.argtypes = [C.c_void_p, C.c_int, C.c_void_p, U8Slice, C.c_void_p, C.c_int64]; L.amo_find_all.restype = C.c_int64
+        L.amo_find_all_parallel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, U8Slice, C.c_void_p, C.c_int64, C.c_int]; L.amo_find_all_parallel.restype = C.c_int64
         L.amo_replacer_build.argtypes = [C.POINTER(U8Slice), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(U8Slice), C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
         L.amo_replacer_build.restype = C.c_int
         L.amo_replacer_free.argtypes = [C.c_void_p]
@@ -157,13 +158,15 @@ class Machine:
         arr, s = _hay_slice(hay)
         return bool(lib().amo_contains_all(self.h, self.n, cs, self._lower_ptr(lower), s))
 
-    def find_all(self, hay, cs=CASE_SENSITIVE, lower=None):
+    def find_all(self, hay, cs=CASE_SENSITIVE, lower=None, threads=1, cap=1024):
         """All matches in the reference's callback order, as a structured array (pos, value)."""
         arr, s = _hay_slice(hay)
-        cap = 1024
         while True:
             out = np.empty(cap, dtype=MATCH_DTYPE)
-            n = lib().amo_find_all(self.h, cs, self._lower_ptr(lower), s, out.ctypes.data, cap)
+            if threads > 1:
+                n = lib().amo_find_all_parallel(self.h, cs, self._lower_ptr(lower), s, out.ctypes.data, cap, threads)
+            else:
+                n = lib().amo_find_all(self.h, cs, self._lower_ptr(lower), s, out.ctypes.data, cap)
             if n <= cap:
                 return out[:n]
             cap = int(n)
