@@ -1,15 +1,340 @@
-// am_replacer.cu -- Replacer.build / run / runWithLimit (placeholder until the device passes land).
+// am_replacer.cu -- Replacer.build / run / runWithLimit on the device.
+//
+// Semantics: src/Data/Text/AhoCorasick/Replacer.hs.  Pair i has priority -i (:101-111).  `runWithLimit`
+// (:203-242) loops: scan the whole text, keep only the matches of the best priority below the threshold
+// (`prependMatch` :252-260), sort them (:241), drop the ones that start inside an earlier kept match
+// (`removeOverlap` :191-198), splice the replacement in (`replace` :163-180), lower the threshold, rescan.
+// One pass therefore replaces the occurrences of exactly ONE needle (priorities are distinct).
+//
+// Device formulation of a pass (the text stays in HBM, ping-ponging between two buffers):
+//   1. full scan with the scan kernels of am_kernels.cu -> sorted (end_pos, rank) keys
+//   2. atomicMin over the keys' needle ids above the previous pass's needle -> this pass's needle
+//   3. stream-compact that needle's matches (already ordered by start), compute their start offsets
+//      (IgnoreCase: `skipCodePointsBackwards`, Utf8.hs:256-276, over `lenCodePoints` of the ORIGINAL needle)
+//   4. `replacementLength` (:183-187) over ALL of them, before overlap removal (:240)
+//   5. removeOverlap: cluster heads (no overlap with the predecessor) are always kept; one thread walks
+//      each cluster greedily
+//   6. exclusive scan of the length deltas, then a tile-parallel splice copy into the other buffer
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <cstring>
+
 #include "am_api_internal.h"
 
 using namespace am;
 
-struct am_replacer { int dummy; };
+struct am_replacer {
+  am_automaton* automaton = nullptr;
+  int cs = AM_CASE_SENSITIVE;
+  uint64_t n = 0;
+  std::vector<uint32_t> len_bytes, len_cps, repl_off;   // per needle index
+  std::vector<uint8_t> repl_bytes;
+  uint8_t* d_repl = nullptr;
+  bool has_empty = false;
+};
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (cap >= bytes) return AM_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return fail(AM_E_OOM, "cudaMalloc(replacer scratch)"); }
+    cap = want; return AM_OK;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct RankIs {
+  uint64_t mask; uint32_t rank;
+  __host__ __device__ bool operator()(const uint64_t& k) const { return (uint32_t)(k & mask) == rank; }
+};
+
+__global__ void best_needle_kernel(const uint64_t* keys, uint64_t n, uint64_t mask, const uint32_t* id_of_rank, long long prev_id, unsigned int* best) {
+  unsigned int local = 0xFFFFFFFFu;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t id = __ldg(id_of_rank + (uint32_t)(keys[i] & mask));
+    if ((long long)id > prev_id && id < local) local = id;
+  }
+  for (int o = 16; o > 0; o >>= 1) { unsigned int v = __shfl_down_sync(0xFFFFFFFFu, local, o); if (v < local) local = v; }
+  if ((threadIdx.x & 31) == 0 && local != 0xFFFFFFFFu) atomicMin(best, local);
+}
+
+// start / length of every match of the pass's needle + sum of the length deltas (replacementLength)
+__global__ void starts_kernel(const uint64_t* sel, uint64_t n, uint32_t rank_bits, const uint8_t* text, int ignore_case,
+                              uint32_t len_bytes, uint32_t len_cps, long long repl_len, uint64_t* start, uint64_t* end,
+                              long long* delta_sum, int* error) {
+  long long local = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t pos = sel[i] >> rank_bits;
+    uint64_t s;
+    if (!ignore_case) {
+      s = pos - len_bytes;                                   // makeMatch CaseSensitive (:268-269)
+    } else {
+      // makeMatch IgnoreCase (:271-274): skipCodePointsBackwards haystack (pos - 1) (lenc - 1)
+      long long idx = (long long)pos - 1, k = (long long)len_cps - 1;
+      for (;;) {
+        if (idx >= 0 && (text[idx] & 0xC0) == 0x80) { idx--; continue; }
+        if (k == 0 || idx < 0) break;
+        idx--; k--;
+      }
+      if (idx < 0) { *error = 1; idx = 0; }
+      s = (uint64_t)idx;
+    }
+    start[i] = s; end[i] = pos;
+    local += repl_len - (long long)(pos - s);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd((unsigned long long*)delta_sum, (unsigned long long)local);
+}
+
+// removeOverlap (:191-198).  A match that does not overlap its predecessor is kept no matter what happened
+// before it, so it heads an independent cluster; inside a cluster the greedy rule is applied serially.
+__global__ void overlap_kernel(const uint64_t* start, const uint64_t* end, uint64_t n, uint8_t* keep) {
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+    if (j > 0 && start[j] < end[j - 1]) continue;            // not a cluster head
+    keep[j] = 1;
+    uint64_t last_end = end[j];
+    for (uint64_t k = j + 1; k < n; k++) {
+      if (start[k] >= end[k - 1]) break;                      // next cluster
+      if (start[k] >= last_end) { keep[k] = 1; last_end = end[k]; } else keep[k] = 0;
+    }
+  }
+}
+
+__global__ void gather_kept_kernel(const uint64_t* start, const uint64_t* end, const uint8_t* keep, const uint64_t* kept_index /*exclusive scan of keep*/,
+                                   uint64_t n, long long repl_len, uint64_t* k_start, uint64_t* k_end, long long* k_delta) {
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+    if (!keep[j]) continue;
+    const uint64_t k = kept_index[j];
+    k_start[k] = start[j]; k_end[k] = end[j]; k_delta[k] = repl_len - (long long)(end[j] - start[j]);
+  }
+}
+
+// `replace` (:163-180) as a tile-parallel splice: each CTA owns SPLICE_TILE source bytes, finds the kept
+// matches that intersect it and copies the gaps between them, shifted by the prefix sum of the deltas.
+// The CTA that owns a match's first byte (or, for an empty match, its position) writes the replacement.
+constexpr int SPLICE_TILE = 1 << 16;
+__global__ void __launch_bounds__(256) splice_kernel(const uint8_t* src, uint64_t src_len, uint8_t* dst, const uint64_t* k_start, const uint64_t* k_end,
+                                                     const long long* k_shift /*exclusive prefix of deltas*/, uint64_t K, const uint8_t* repl, uint32_t repl_len,
+                                                     long long total_shift) {
+  const uint64_t t0 = (uint64_t)blockIdx.x * SPLICE_TILE;
+  const uint64_t t1 = t0 + SPLICE_TILE < src_len ? t0 + SPLICE_TILE : src_len;
+  const bool last_tile = t1 == src_len;
+  // first kept match whose END is > t0, or whose start is >= t0 (covers empty matches at t0)
+  uint64_t lo = 0, hi = K;
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (k_end[mid] > t0 || k_start[mid] >= t0) hi = mid; else lo = mid + 1; }
+  uint64_t k = lo;
+  uint64_t cur = t0;                                        // next source byte to place
+  // a match that began in an earlier tile and extends into this one swallows our first bytes
+  if (k < K && k_start[k] < t0) { cur = k_end[k] < t1 ? k_end[k] : t1; k++; }
+  for (;;) {
+    const bool have = k < K && (k_start[k] < t1 || (last_tile && k_start[k] == t1));
+    const uint64_t gap_end = have ? k_start[k] : t1;
+    if (gap_end > cur) {                                    // copy source [cur, gap_end)
+      const long long shift = k < K ? k_shift[k] : total_shift;
+      for (uint64_t x = cur + threadIdx.x; x < gap_end; x += blockDim.x) dst[(long long)x + shift] = src[x];
+    }
+    if (!have) break;
+    const long long at = (long long)k_start[k] + k_shift[k];
+    for (uint32_t r = threadIdx.x; r < repl_len; r += blockDim.x) dst[at + r] = repl[r];
+    cur = k_end[k] < t1 ? k_end[k] : t1;
+    if (k_end[k] > t1) break;                               // the rest of the tile is inside this match
+    k++;
+  }
+}
+
+}  // namespace
 
 extern "C" {
-int am_replacer_build(const am_u8slice*, const am_u8slice*, size_t, int, const am_lower_table*, const am_options*, am_replacer** out) {
-  if (out) *out = nullptr;
-  return fail(AM_E_UNSUPPORTED, "replacer not built yet");
+
+int am_replacer_build(const am_u8slice* needles, const am_u8slice* repls, size_t n, int cs, const am_lower_table* lower,
+                      const am_options* opts, am_replacer** out) {
+  if (!out) return fail(AM_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n > 0 && (!needles || !repls)) return fail(AM_E_BADARG, "needles / replacements is null");
+  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) return fail(AM_E_BADARG, "unknown case sensitivity");
+  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table");
+  am_replacer* r = new am_replacer();
+  r->cs = cs; r->n = n;
+  LowerTable lt;
+  int rc = build_lower_table(cs == AM_IGNORE_CASE ? lower : nullptr, &lt);
+  if (rc) { delete r; return fail(rc, "bad lower table"); }
+  std::vector<std::vector<uint8_t>> built(n);
+  std::vector<am_u8slice> slices(n);
+  r->repl_off.assign(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (needles[i].len < 0 || repls[i].len < 0 || (needles[i].len && !needles[i].ptr) || (repls[i].len && !repls[i].ptr)) { delete r; return fail(AM_E_BADARG, "bad slice"); }
+    const uint8_t* d = needles[i].ptr + needles[i].off;
+    uint32_t cps = 0;
+    for (int64_t k = 0; k < needles[i].len; k++) cps += (d[k] & 0xC0) != 0x80;
+    r->len_bytes.push_back((uint32_t)needles[i].len);            // needleLengthBytes of the ORIGINAL needle (:112)
+    r->len_cps.push_back(cps);                                    // needleLengthCodePoints (:113)
+    if (needles[i].len == 0) r->has_empty = true;
+    if (cs == AM_IGNORE_CASE) lower_utf8_host(lt, d, needles[i].len, &built[i]);   // Utf8.lowerUtf8 needle (:107)
+    else built[i].assign(d, d + needles[i].len);
+    slices[i] = am_u8slice{built[i].data(), 0, (int64_t)built[i].size()};
+    r->repl_bytes.insert(r->repl_bytes.end(), repls[i].ptr + repls[i].off, repls[i].ptr + repls[i].off + repls[i].len);
+    r->repl_off[i + 1] = (uint32_t)r->repl_bytes.size();
+  }
+  if (cs == AM_IGNORE_CASE && r->has_empty) {
+    delete r;
+    return fail(AM_E_UNSUPPORTED, "empty needle in an IgnoreCase replacer: the reference's skipCodePointsBackwards diverges on it");
+  }
+  rc = am_automaton_build(slices.data(), n, cs, lower, opts, &r->automaton);
+  if (rc) { delete r; return rc; }
+  if (r->automaton->device >= 0) {
+    cudaSetDevice(r->automaton->device);
+    if (cudaMalloc((void**)&r->d_repl, r->repl_bytes.size() + 16) != cudaSuccess) { cudaGetLastError(); am_replacer_free(r); return fail(AM_E_OOM, "cudaMalloc(replacements)"); }
+    if (!r->repl_bytes.empty()) cudaMemcpy(r->d_repl, r->repl_bytes.data(), r->repl_bytes.size(), cudaMemcpyHostToDevice);
+  }
+  *out = r;
+  return AM_OK;
 }
-void am_replacer_free(am_replacer* r) { delete r; }
-int am_replacer_run(const am_replacer*, am_u8slice, uint64_t, uint8_t**, uint64_t*, int*) { return fail(AM_E_UNSUPPORTED, "replacer not built yet"); }
+
+void am_replacer_free(am_replacer* r) {
+  if (!r) return;
+  if (r->d_repl) cudaFree(r->d_repl);
+  if (r->automaton) am_automaton_free(r->automaton);
+  delete r;
 }
+
+int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint8_t** out, uint64_t* out_len, int* exceeded) {
+  if (!r || !out || !out_len || !exceeded) return fail(AM_E_BADARG, "null argument");
+  if (hay.len < 0 || hay.off < 0 || (hay.len > 0 && !hay.ptr)) return fail(AM_E_BADARG, "bad text slice");
+  const am_automaton* a = r->automaton;
+  int rc = check_ready(a); if (rc) return rc;
+  *out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0;
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = 0;
+  DevBuf text_a, text_b, sel, starts, ends, keep, kidx, kstart, kend, kdelta, kshift, cubtmp, scal;
+  uint64_t len = (uint64_t)hay.len;
+  auto done = [&](int code) { release_ws(a, ws); return code; };
+  if ((rc = text_a.ensure(len + 64)) || (rc = scal.ensure(64))) return done(rc);
+  if (len) {
+    cudaError_t e = cudaMemcpyAsync(text_a.p, hay.ptr + hay.off, len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return done(cuda_fail(e, "H2D text"));
+  }
+  DevBuf* cur = &text_a; DevBuf* nxt = &text_b;
+  const uint32_t rank_bits = a->host.rank_bits;
+  const uint64_t mask = (1ull << rank_bits) - 1;
+  long long prev_id = -1;                          // threshold 1 keeps every priority (:211)
+  const long long last_id = (long long)r->n - 1;   // minPriority = 1 - numNeedles (:217)
+  struct Scalars { unsigned int best; int error; long long delta_sum; unsigned long long nsel; unsigned long long nkept; };
+  Scalars* d_s = scal.as<Scalars>();
+  Scalars h_s;
+
+  for (;;) {
+    // ---- 1. scan the current text --------------------------------------------------------------------
+    am_dev_text t{cur->p, len, 0, 0};
+    uint64_t n = 0;
+    if ((rc = find_all_sorted(a, ws, t, st, &n))) return done(rc);
+    g_last_passes++;
+    if (n == 0) break;                             // (_, []) -> Just haystack (:230)
+    // ---- 2. the best priority below the threshold ------------------------------------------------------
+    h_s = Scalars{0xFFFFFFFFu, 0, 0, 0, 0};
+    cudaMemcpyAsync(d_s, &h_s, sizeof h_s, cudaMemcpyHostToDevice, st);
+    {
+      unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+      g_kernel_launches++;
+      best_needle_kernel<<<blocks, 256, 0, st>>>(ws->keys_b, n, mask, a->dev.id_of_rank, prev_id, &d_s->best);
+    }
+    cudaMemcpyAsync(&h_s, d_s, sizeof h_s, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(cuda_fail(e, "best needle"));
+    if (h_s.best == 0xFFFFFFFFu) break;            // nothing below the threshold
+    const uint32_t id = h_s.best;
+    const uint32_t rank = a->host.rank_of_id[id];
+    const uint32_t rl = r->repl_off[id + 1] - r->repl_off[id];
+    // ---- 3. this needle's matches, in order ------------------------------------------------------------
+    if ((rc = sel.ensure(n * 8))) return done(rc);
+    size_t tb = 0;
+    RankIs pred{mask, rank};
+    cub::DeviceSelect::If(nullptr, tb, ws->keys_b, sel.as<uint64_t>(), &d_s->nsel, (int64_t)n, pred, st);
+    if ((rc = cubtmp.ensure(tb))) return done(rc);
+    cub::DeviceSelect::If(cubtmp.p, tb, ws->keys_b, sel.as<uint64_t>(), &d_s->nsel, (int64_t)n, pred, st);
+    cudaMemcpyAsync(&h_s, d_s, sizeof h_s, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "select"));
+    const uint64_t ns = h_s.nsel;
+    if ((rc = starts.ensure(ns * 8)) || (rc = ends.ensure(ns * 8)) || (rc = keep.ensure(ns + 8)) || (rc = kidx.ensure(ns * 8 + 8)) ||
+        (rc = kstart.ensure(ns * 8)) || (rc = kend.ensure(ns * 8)) || (rc = kdelta.ensure(ns * 8)) || (rc = kshift.ensure(ns * 8 + 8)))
+      return done(rc);
+    {
+      unsigned blocks = (unsigned)std::min<uint64_t>((ns + 127) / 128, 148 * 8);
+      g_kernel_launches++;
+      starts_kernel<<<blocks, 128, 0, st>>>(sel.as<uint64_t>(), ns, rank_bits, cur->as<uint8_t>(), r->cs == AM_IGNORE_CASE, r->len_bytes[id], r->len_cps[id],
+                                            (long long)rl, starts.as<uint64_t>(), ends.as<uint64_t>(), &d_s->delta_sum, &d_s->error);
+    }
+    // ---- 4. replacementLength over the un-deoverlapped matches (:240) -----------------------------------
+    cudaMemcpyAsync(&h_s, d_s, sizeof h_s, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "starts"));
+    if (h_s.error) return done(fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards (text is not valid UTF-8?)"));
+    if (max_len != UINT64_MAX) {
+      const long long would = (long long)len + h_s.delta_sum;
+      if (would > 0 && (uint64_t)would > max_len) { *exceeded = 1; return done(AM_OK); }
+    }
+    // ---- 5. removeOverlap ----------------------------------------------------------------------------------
+    cudaMemsetAsync(keep.p, 0, ns + 8, st);
+    {
+      unsigned blocks = (unsigned)std::min<uint64_t>((ns + 127) / 128, 148 * 8);
+      g_kernel_launches++;
+      overlap_kernel<<<blocks, 128, 0, st>>>(starts.as<uint64_t>(), ends.as<uint64_t>(), ns, keep.as<uint8_t>());
+    }
+    tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, keep.as<uint8_t>(), kidx.as<uint64_t>(), (int64_t)ns + 1, st);
+    if ((rc = cubtmp.ensure(tb))) return done(rc);
+    cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, keep.as<uint8_t>(), kidx.as<uint64_t>(), (int64_t)ns + 1, st);   // kidx[ns] = #kept
+    cudaMemcpyAsync(&h_s.nkept, kidx.as<uint64_t>() + ns, 8, cudaMemcpyDeviceToHost, st);
+    {
+      unsigned blocks = (unsigned)std::min<uint64_t>((ns + 255) / 256, 148 * 8);
+      g_kernel_launches++;
+      gather_kept_kernel<<<blocks, 256, 0, st>>>(starts.as<uint64_t>(), ends.as<uint64_t>(), keep.as<uint8_t>(), kidx.as<uint64_t>(), ns, (long long)rl,
+                                                 kstart.as<uint64_t>(), kend.as<uint64_t>(), kdelta.as<long long>());
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "overlap"));
+    const uint64_t K = h_s.nkept;
+    // ---- 6. splice -------------------------------------------------------------------------------------------
+    tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, kdelta.as<long long>(), kshift.as<long long>(), (int64_t)K, st);
+    if ((rc = cubtmp.ensure(tb))) return done(rc);
+    cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, kdelta.as<long long>(), kshift.as<long long>(), (int64_t)K, st);
+    long long last_shift = 0, last_delta = 0;
+    if (K) {
+      cudaMemcpyAsync(&last_shift, kshift.as<long long>() + (K - 1), 8, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&last_delta, kdelta.as<long long>() + (K - 1), 8, cudaMemcpyDeviceToHost, st);
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "scan"));
+    const long long total_shift = last_shift + last_delta;
+    const uint64_t new_len = (uint64_t)((long long)len + total_shift);
+    if ((rc = nxt->ensure(new_len + 64))) return done(rc);
+    {
+      uint64_t tiles = (len + SPLICE_TILE - 1) / SPLICE_TILE;
+      if (tiles == 0) tiles = 1;                                  // empty text with an empty-needle match
+      g_kernel_launches++;
+      splice_kernel<<<(unsigned)tiles, 256, 0, st>>>(cur->as<uint8_t>(), len, nxt->as<uint8_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), kshift.as<long long>(), K,
+                                                     r->d_repl + r->repl_off[id], rl, total_shift);
+      if ((e = cudaGetLastError()) != cudaSuccess) return done(cuda_fail(e, "splice launch"));
+    }
+    std::swap(cur, nxt);
+    len = new_len;
+    if ((long long)id == last_id) break;           // p == minPriority: no needle is left (:241)
+    prev_id = id;                                   // go p (:242)
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(cuda_fail(e, "replacer"));
+  uint8_t* host = static_cast<uint8_t*>(std::malloc(len ? len : 1));
+  if (!host) return done(fail(AM_E_OOM, "malloc(result)"));
+  if (len) {
+    e = cudaMemcpy(host, cur->p, len, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { std::free(host); return done(cuda_fail(e, "D2H result")); }
+  }
+  *out = host; *out_len = len;
+  return done(AM_OK);
+}
+
+}  // extern "C"

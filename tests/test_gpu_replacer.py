@@ -1,0 +1,84 @@
+"""Replacer.build / run / runWithLimit on the device vs the reference's vectors and the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def am():
+    import alfred_margaret_b200 as pkg
+    from alfred_margaret_b200 import _ffi
+    assert _ffi.lib().am_device_count() >= 1
+    return pkg
+
+
+def test_golden_replacer(am, golden):
+    R = am.replacer
+    for v in golden["replacer"]:
+        r = R.build(v["cs"], [tuple(p) for p in v["pairs"]])
+        assert R.run(r, v["haystack"]).decode("utf-8") == v["expected"], v["src"]
+
+
+def test_run_with_limit(am):
+    R = am.replacer
+    r = R.build(0, [("a", "bbbb")])
+    assert R.run_with_limit(r, 8, "aa") == b"bbbbbbbb"
+    assert R.run_with_limit(r, 7, "aa") is None                      # Replacer.hs:240
+    r = R.build(0, [("aaa", "xxxxx")])                               # replacementLength BEFORE removeOverlap
+    assert R.run_with_limit(r, 6, "aaaa") is None and R.run_with_limit(r, 8, "aaaa") == b"xxxxxa"
+    with pytest.raises(am._ffi.AmError):
+        R.build(1, [("", "x")])                                      # empty needle + IgnoreCase: reference diverges
+
+
+def test_properties_vs_oracle(am, oracle, lower_dense):
+    """AhoCorasickSpec.hs:137-163 generators; every result compared with the oracle's Replacer."""
+    R = am.replacer
+    rng = np.random.default_rng(17)
+    alpha = "abAB"
+    def gen_hay(maxlen):
+        return "".join(("İ" if rng.random() < 0.03 else ("ß" if rng.random() < 0.02 else alpha[int(rng.integers(0, 4))])) for _ in range(int(rng.integers(0, maxlen))))
+    def gen_pairs():
+        return [("".join(alpha[int(i)] for i in rng.integers(0, 4, size=int(rng.integers(1, 4)))),
+                 "".join(alpha[int(i)] for i in rng.integers(0, 4, size=int(rng.integers(0, 4))))) for _ in range(int(rng.integers(0, 5)))]
+    for it in range(120):
+        hay, p1, p2 = gen_hay(40), gen_pairs(), gen_pairs()
+        for cs in (0, 1):
+            o12 = oracle.Replacer(p1 + p2, cs=cs, lower=lower_dense).run(hay)
+            r1, r2 = R.build(cs, p1), R.build(cs, p2)
+            r12 = R.compose(r1, r2)
+            got = R.run(r12, hay)
+            assert got == o12, (cs, p1, p2, hay)
+            assert R.run(r2, R.run(r1, hay)) == got                    # compose law (:137-148)
+        expected = hay
+        for n, rep in p1:
+            expected = expected.replace(n, rep)
+        assert R.run(R.build(0, p1), hay).decode("utf-8") == expected  # == sequential Text.replace (:154-163)
+    assert R.compose(R.build(0, []), R.build(1, [])) is None
+
+
+def test_overlap_chains_and_empty_needle(am, oracle):
+    R = am.replacer
+    for pairs, hay in [([("aaa", "b")], "a" * 100001), ([("aa", "a")], "a" * 5000), ([("ab", ""), ("ba", "x")], "ab" * 3000 + "a"),
+                       ([("", "-"), ("b", "")], "abcabc"), ([("abc", "abcabc")], "abc" * 2000)]:
+        assert R.run(R.build(0, pairs), hay) == oracle.Replacer(pairs).run(hay), pairs
+
+
+def test_config4_downscaled(am, oracle):
+    """BASELINE.json config 4 down-scaled: 300 (needle, replacement) pairs, 8 MiB a-z haystack with plants;
+    result bytes and pass count identical to the oracle."""
+    from alfred_margaret_b200 import synth
+    rng = np.random.default_rng(62)
+    needles = synth.random_needles(300, 62, 4, 12)
+    repls = [bytes(rng.integers(ord("A"), ord("Z") + 1, size=int(rng.integers(0, 16)), dtype=np.uint8)) for _ in needles]
+    for i in range(0, 300, 20):     # cascading: some replacements contain a lower-priority needle
+        repls[i] = repls[i][:3] + needles[(i + 7) % 300]
+    hay = synth.fill_host(0, 8 << 20, 63)
+    synth.plant_host(hay, 0, 64, needles[:64])
+    pairs = list(zip(needles, repls))
+    o = oracle.Replacer(pairs)
+    want = o.run(hay)
+    r = am.replacer.build(0, pairs)
+    got = am.replacer.run(r, hay)
+    assert got == want
+    assert r.last_passes == o.passes
