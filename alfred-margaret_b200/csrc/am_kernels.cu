@@ -172,7 +172,11 @@ constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors 
 //   FK_PF         distance (in CTA tiles) of the bulk L2 prefetch issued ahead of the streaming loads; the
 //                 register double-buffer alone keeps too few bytes in flight to cover HBM latency
 #ifndef FK_PF
-#define FK_PF 2
+#define FK_PF 0
+#endif
+//   FK_DEBUG      compile the stage-isolation switches (AM_DEBUG_FLAGS=1: probes only, 2: no survivor walk)
+#ifndef FK_DEBUG
+#define FK_DEBUG 0
 #endif
 constexpr int FK_CQ = 128;                       // dense pop: candidate queue entries per warp
 
@@ -263,12 +267,8 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
 
 // Drain the warp's survivor queue (warp converged on entry and exit).
 template <int MODE>
-__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
-                                         unsigned long long& local_count, uint32_t min_fill) {
-  __syncwarp();
-  uint32_t n = sm->sq_n[c.warp];
-  if (n > FK_SQ) n = FK_SQ;
-  if (n < min_fill || n == 0) return;
+__device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                           unsigned long long& local_count, uint32_t n) {
   for (uint32_t k = c.lane; k < n; k += 32) {
     const uint2 e = sm->sq[c.warp][k];
     fk_deep_verify<MODE>(A, a, sm, c, e.x, e.y, local_count);
@@ -277,6 +277,16 @@ __device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& 
   if (c.lane == 0) sm->sq_n[c.warp] = 0;
   __syncwarp();
   if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
+}
+
+template <int MODE>
+__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                         unsigned long long& local_count, uint32_t min_fill) {
+  __syncwarp();
+  uint32_t n = sm->sq_n[c.warp];
+  if (n > FK_SQ) n = FK_SQ;
+  if (n < min_fill || n == 0) return;
+  fk_drain_body<MODE>(A, a, sm, c, local_count, n);
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -393,40 +403,70 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
   unsigned long long local_count = 0;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
+  // Software pipeline over (tile, pair): everything a pair needs was requested one pair earlier -- its two
+  // granules per lane and the word that follows the pair -- including across chunk and tile boundaries.
+  // Interior tiles (everything they and their successor's first pair touch lies inside the text) use
+  // unguarded loads at immediate offsets from one per-lane pointer; edge tiles take the guarded path.
+  auto pair_granule = [&](uint64_t tile, int pair) -> uint64_t {   // first 16-byte granule of (tile, pair) for this warp
+    return ((v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK) >> 4) + (uint64_t)pair * 64;
+  };
+  auto load_pair_guarded = [&](uint64_t g, uint4& A, uint4& B, uint32_t& tail) {
+    A = zero4; B = zero4; tail = 0;
+    if (g + lane < nvec) A = ld_stream_v4(base16 + g + lane);
+    if (g + 32 + lane < nvec) B = ld_stream_v4(base16 + g + 32 + lane);
+    if (lane == 0 && g + 64 < nvec) tail = __ldg(c.base32 + (g + 64) * 4);
+  };
+  uint4 cA = zero4, cB = zero4;
+  uint32_t tail_cur = 0;
+  if (blockIdx.x < num_tiles) load_pair_guarded(pair_granule(blockIdx.x, 0), cA, cB, tail_cur);
+  const uint64_t tile_stride_granules = (uint64_t)gridDim.x * (FK_TILE / 16);
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
     const uint64_t chunk_v0 = v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK;  // granule-aligned virtual index
     const uint32_t chunk_rel = (uint32_t)(chunk_v0 - v_begin);
+    const uint64_t g0 = chunk_v0 >> 4;
+    const bool has_next = tile + gridDim.x < num_tiles;
+    // last granule touched from this tile: the tail word of the NEXT tile's first pair (or of our last pair)
+    const bool interior = (has_next ? g0 + tile_stride_granules + 64 + 1 : g0 + FK_PAIRS * 64 + 1) < nvec;
+    const uint4* pl = base16 + g0 + lane;
 #if FK_PF > 0
     if (lane == 0) {   // pull this warp's chunk of a later tile into L2 (one TMA-style bulk prefetch, no registers)
-      const uint64_t pv = (chunk_v0 + (uint64_t)FK_PF * gridDim.x * FK_TILE) >> 4;
+      const uint64_t pv = g0 + (uint64_t)FK_PF * tile_stride_granules;
       if (tile + (uint64_t)FK_PF * gridDim.x < num_tiles && pv + FK_CHUNK / 16 <= nvec)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base16 + pv), "r"((uint32_t)FK_CHUNK) : "memory");
     }
 #endif
-    uint64_t vec = (chunk_v0 >> 4) + lane;                // this lane's granule of iteration A of the pair
-    uint4 cA = vec < nvec ? ld_stream_v4(base16 + vec) : zero4;
-    uint4 cB = vec + 32 < nvec ? ld_stream_v4(base16 + vec + 32) : zero4;
+    const uint4* pn = pl + 64;                            // this lane's granule of the NEXT pair
 #pragma unroll 1
     for (int pair = 0; pair < FK_PAIRS; pair++) {
-      // prefetch the next pair (after the chunk only lane 0's first word is needed)
+      // request the next pair (same chunk, or the first pair of this warp's chunk in the CTA's next tile)
       uint4 nA = zero4, nB = zero4;
-      const uint64_t nv = vec + 64;
-      if (pair + 1 < FK_PAIRS) {
-        if (nv < nvec) nA = ld_stream_v4(base16 + nv);
-        if (nv + 32 < nvec) nB = ld_stream_v4(base16 + nv + 32);
-      } else if (lane == 0 && nv < nvec) nA.x = __ldg(c.base32 + nv * 4);
+      uint32_t tail_next = 0;
+      const bool same = pair + 1 < FK_PAIRS;
+      if (interior) {
+        if (!same) pn = pl + tile_stride_granules;
+        if (same || has_next) {
+          nA = ld_stream_v4(pn);
+          nB = ld_stream_v4(pn + 32);
+          if (lane == 0) tail_next = __ldg(reinterpret_cast<const uint32_t*>(pn + 64));
+        }
+        pn += 64;
+      } else if (same || has_next) {
+        load_pair_guarded(pair_granule(same ? tile : tile + gridDim.x, same ? pair + 1 : 0), nA, nB, tail_next);
+      }
       // mirror the pair into the window (exact q-gram recovery for the few candidates)
       reinterpret_cast<uint4*>(win)[lane] = cA;
       reinterpret_cast<uint4*>(win)[32 + lane] = cB;
-      if (lane == 0) win[256] = nA.x;
+      if (lane == 0) win[256] = tail_cur;
       const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
-      const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? nA.x : cB.x, (lane + 1) & 31);
+      const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail_cur : cB.x, (lane + 1) & 31);
       uint32_t m = 0;                                      // bit (31 - P) <-> position P of the lane's 32
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
       __syncwarp();
+#if FK_DEBUG
       if (a.debug & 1u) { local_count += __popc(m); m = 0; }
+#endif
       const uint32_t pair_rel = chunk_rel + (uint32_t)pair * 1024u;
 #if FK_POP_DENSE
       {
@@ -470,7 +510,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
             const uint32_t o = cq[k];
             uint32_t g;
             if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
-              if (a.debug & 2u) { local_count++; continue; }
+    #if FK_DEBUG
+          if (a.debug & 2u) { local_count++; continue; }
+#endif
               const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
               if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
               else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);
@@ -486,7 +528,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
         const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);   // byte offset inside the pair
         uint32_t g;
         if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
+#if FK_DEBUG
           if (a.debug & 2u) { local_count++; continue; }
+#endif
           const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
           if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
           else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);   // queue full: verify in place
@@ -494,7 +538,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
       }
 #endif
       fk_drain<MODE>(A, a, sm, c, local_count, 32);       // only when a full round of survivors waits
-      cA = nA; cB = nB; vec = nv;
+      cA = nA; cB = nB; tail_cur = tail_next;
     }
   }
   fk_drain<MODE>(A, a, sm, c, local_count, 1);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B the filter-kernel build variants (development aid): parity smoke + stage-isolated timings.
 cd "$(dirname "$0")/.."
-for v in ${VARIANTS:-""}; do
+for v in ${VARIANTS:-_dbg}; do
   export AM_LIB=$PWD/alfred-margaret_b200/lib/libam_b200$v.so
   echo "=== variant '$v'"
   python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
