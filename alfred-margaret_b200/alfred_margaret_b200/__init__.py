@@ -4,5 +4,5 @@ Module names follow the reference (Data.Text.AhoCorasick.{Automaton,Searcher,Rep
 Data.Text.Utf8, Data.Text.CaseSensitivity).  All matching runs in the CUDA library; importing the
 FFI without the built library raises ImportError (no CPU fallback).
 """
-from . import automaton, case_sensitivity, replacer, searcher, sharded, synth, utf8  # noqa: F401
+from . import automaton, case_sensitivity, replacer, searcher, sharded, splitter, synth, utf8  # noqa: F401
 from .case_sensitivity import CaseSensitive, CaseSensitivity, IgnoreCase  # noqa: F401

@@ -164,11 +164,7 @@ constexpr int FK_SQ = 64;                        // survivor queue entries per w
 constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
 constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
 // Build-time variants (A/B-tested on the GPU):
-//   FK_POP_DENSE  compact candidates with a warp scan and test them 32 at a time, instead of each lane
-//                 popping and testing its own candidates
-#ifndef FK_POP_DENSE
-#define FK_POP_DENSE 0
-#endif
+//   (a warp-scan "dense" compaction of the candidates was A/B-tested and was not faster; removed)
 //   FK_PF         distance (in CTA tiles) of the bulk L2 prefetch issued ahead of the streaming loads; the
 //                 register double-buffer alone keeps too few bytes in flight to cover HBM latency
 #ifndef FK_PF
@@ -178,7 +174,6 @@ constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors 
 #ifndef FK_DEBUG
 #define FK_DEBUG 0
 #endif
-constexpr int FK_CQ = 128;                       // dense pop: candidate queue entries per warp
 
 struct FilterSmem {
   uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
@@ -186,10 +181,6 @@ struct FilterSmem {
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
   uint2 sq[FK_WARPS][FK_SQ];                     // 16 KiB: (offset from v_begin, q-gram)
   unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
-#if FK_POP_DENSE
-  uint16_t cq[FK_WARPS][FK_CQ];                  // 8 KiB: candidate offsets inside the pair
-  uint32_t cq_n[FK_WARPS];
-#endif
   uint32_t sq_n[FK_WARPS];
   uint32_t wkeys_n[FK_WARPS];
   unsigned long long red[FK_WARPS];
@@ -300,10 +291,11 @@ template <bool Q4>
 __device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmask, uint32_t krow, uint32_t m,
                                                uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
+  // positions are visited last-to-first so that, after both granules, bit P of the mask is position P
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
+  for (int k = 3; k >= 0; k--) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 3; j >= 0; j--) {
       uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
       if (!Q4) g &= qmask;
 #if FK_WB
@@ -376,12 +368,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
                    "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
   }
-  if (lane == 0) {
-    sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0;
-#if FK_POP_DENSE
-    sm->cq_n[warp] = 0;
-#endif
-  }
+  if (lane == 0) { sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0; }
   __syncthreads();
   {
     uint32_t done = 0;
@@ -460,72 +447,19 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
       if (lane == 0) win[256] = tail_cur;
       const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
       const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail_cur : cB.x, (lane + 1) & 31);
-      uint32_t m = 0;                                      // bit (31 - P) <-> position P of the lane's 32
-      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
+      uint32_t m = 0;                                      // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
+      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
       __syncwarp();
 #if FK_DEBUG
       if (a.debug & 1u) { local_count += __popc(m); m = 0; }
 #endif
       const uint32_t pair_rel = chunk_rel + (uint32_t)pair * 1024u;
-#if FK_POP_DENSE
-      {
-        // ---- compact the candidate offsets with a warp scan, then test them 32 at a time ----------------
-        const uint32_t cnt = __popc(m);
-#if FK_POP_DENSE == 2
-        // slot allocation with one shared-memory atomic per lane that has candidates
-        uint32_t incl = cnt;
-        if (cnt) incl += atomicAdd(&sm->cq_n[warp], cnt);
-        __syncwarp();
-        const uint32_t total = sm->cq_n[warp];
-        __syncwarp();
-        if (lane == 0) sm->cq_n[warp] = 0;
-#else
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += n; }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-#endif
-        if (total > FK_CQ) {
-          // pathological density: every lane tests its own candidates
-          while (m) {
-            const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
-            const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);
-            uint32_t g;
-            if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
-              const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-              if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
-              else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);
-            }
-          }
-        } else if (total) {
-          uint16_t* cq = sm->cq[warp];
-          uint32_t pos = incl - cnt;
-          while (m) {
-            const uint32_t P = __clz(m); m &= ~(0x80000000u >> P);
-            cq[pos++] = (uint16_t)(((P & 16u) << 5) | (lane << 4) | (P & 15u));
-          }
-          __syncwarp();
-          for (uint32_t k = lane; k < total; k += 32) {
-            const uint32_t o = cq[k];
-            uint32_t g;
-            if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
-    #if FK_DEBUG
-          if (a.debug & 2u) { local_count++; continue; }
-#endif
-              const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-              if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
-              else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);
-            }
-          }
-        }
-      }
-#else
       // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
       while (m) {
-        const uint32_t P = __clz(m);
-        m &= ~(0x80000000u >> P);
-        const uint32_t o = ((P & 16u) << 5) | (lane << 4) | (P & 15u);   // byte offset inside the pair
+        const uint32_t P = 31u - __clz(m);                    // FLO: highest candidate position
+        m ^= 1u << P;
+        const uint32_t o = (P & 16u) * 31u + P + (lane << 4);  // byte offset inside the pair: (P >> 4) * 512 + lane * 16 + (P & 15)
         uint32_t g;
         if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
 #if FK_DEBUG
@@ -536,7 +470,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
           else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);   // queue full: verify in place
         }
       }
-#endif
       fk_drain<MODE>(A, a, sm, c, local_count, 32);       // only when a full round of survivors waits
       cA = nA; cB = nB; tail_cur = tail_next;
     }

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, uint32_t p0, uint32_
       if (KIND == 12) a[j] = *(const uint32_t*)(smb + ((a[j] & 0x7FC0u) | (lane4 & 0x3C))) + j;  // LDS 16 copies (2-way conflicts)
       if (KIND == 13) a[j] = *(const uint32_t*)(smb + (a[j] & 0x7FFCu)) + j;  // LDS fully shared random
       if (KIND == 14) { uint32_t y = (a[j] * 0x9E3779B1u) >> 15; uint32_t w = *(const uint32_t*)(smb + ((y & 0x7F80u) | lane4)); uint32_t t = __funnelshift_l(w, w, y); a[j] = __funnelshift_l(t, a[j], 1) + j; }  // full probe
+      if (KIND == 16) { uint32_t x = a[j] * 0x9E3779B1u; uint32_t w = *(const uint32_t*)(smb + ((x >> 21) * p1 + lane4)); uint32_t t = __funnelshift_l(w, w, x); a[j] = __funnelshift_l(t, a[j], 1) + j; }  // WB probe: IMAD,SHF,IMAD,LDS,SHF,SHF
+      if (KIND == 17) { unsigned long long xx = (unsigned long long)(a[j] * 0x9E3779B1u) * (unsigned long long)p2; uint32_t w = *(const uint32_t*)(smb + ((uint32_t)(xx >> 32) * p1 + lane4)); uint32_t t = __funnelshift_l(w, w, (uint32_t)xx); a[j] = __funnelshift_l(t, a[j], 1) + j; }  // row via IMAD.WIDE hi
       if (KIND == 15) { uint32_t y = __umulhi(a[j] * 0x9E3779B1u, p1); uint32_t w = *(const uint32_t*)(smb + ((y & 0x7F80u) | lane4)); uint32_t t = __funnelshift_l(w, w, y); a[j] = __funnelshift_l(t, a[j], 1) + j; }  // probe, y via IMAD.HI
     }
   }
@@ -46,10 +48,10 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, uint32_t p0, uint32_
 template <int KIND> void run(const char* name, int ops_per_inner) {
   uint32_t* d; cudaMalloc(&d, 4);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<KIND><<<148, 1024>>>(d, 3, 1u << 17, 5);
+  k<KIND><<<148, 1024>>>(d, 3, KIND >= 16 ? 4u : 1u << 17, KIND == 17 ? 16u : 5);
   cudaDeviceSynchronize();
   cudaEventRecord(e0);
-  k<KIND><<<148, 1024>>>(d, 3, 1u << 17, 5);
+  k<KIND><<<148, 1024>>>(d, 3, KIND >= 16 ? 4u : 1u << 17, KIND == 17 ? 16u : 5);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   double warp_inner = 148.0 * 32 * ITERS * 8;   // warp-level executions of the inner statement
@@ -62,5 +64,6 @@ int main() {
   run<2>("SHF.R.W const", 1); run<3>("SHF.L.W var", 1); run<4>("LOP3", 1); run<6>("PRMT", 1); run<8>("IADD3", 1); run<9>("POPC+IADD", 2);
   run<10>("SHFL", 1); run<5>("LDS private +LOP3+IADD", 3); run<12>("LDS 16copies +LOP3+IADD", 3); run<13>("LDS shared rnd +LOP+IADD", 3);
   run<14>("probe (IMAD,SHF,LOP3,LDS,SHF,SHF,IADD)", 7); run<15>("probe y via IMAD.HI", 7);
+  run<16>("WB probe (IMAD,SHF,IMAD,LDS,SHF,SHF)", 7); run<17>("WB probe, row via IMAD.WIDE", 7);
   return 0;
 }

@@ -235,3 +235,69 @@ def test_config2_downscaled(am, oracle, torch_cuda):
         assert np.array_equal(rec["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(rec["needle_id"].astype(np.int64), want["value"])
     digits = torch.full((1 << 20,), ord("7"), dtype=torch.uint8, device="cuda")      # all-miss haystack
     assert m.contains_any_dev(digits.data_ptr(), digits.numel()) is False
+
+
+def test_golden_splitter(am, golden):
+    """Splitter: AhoCorasickSpec.hs:220-244."""
+    S = am.splitter
+    for v in golden["splitter"]:
+        sp = S.build(v["separator"])
+        got = S.split_ignore_case(sp, v["haystack"]) if v["ignore_case"] else S.split(sp, v["haystack"])
+        assert [x.decode("utf-8") for x in got] == v["expected"], v["src"]
+    # overlapping separators are ignored left to right (stepAccum, Splitter.hs:158-170)
+    assert S.split(S.build("aa"), "aaaaa") == [b"", b"", b"a"]
+    assert S.split(S.build("x"), "") == [b""]
+
+
+def test_config3_downscaled_ignore_case(am, oracle, lower_dense):
+    """BASELINE.json config 3 down-scaled: 2 000 lower-case needles (20 % with non-ASCII code points), IgnoreCase,
+    an 8 MiB mixed-case UTF-8 haystack with 1/2/3/4-byte code points incl. length-changing ones (K, Å, ẞ, İ, Ⱥ)."""
+    rng = np.random.default_rng(52)
+    ascii_l = "abcdefghijklmnopqrstuvwxyz"
+    extra = "éößåяωǳⱥ"
+    needles = set()
+    while len(needles) < 2000:
+        n = int(rng.integers(4, 17))
+        pool = ascii_l + (extra * 3 if rng.random() < 0.2 else "")
+        needles.add("".join(pool[int(i)] for i in rng.integers(0, len(pool), size=n)))
+    needles = sorted(needles)
+    cps = list(ascii_l + ascii_l.upper()) * 6 + list(" .,;-") * 4 + list("éÉöÖßåÅяЯωΩǳǲǱ") * 2 + list("ẞKÅȺⱥİ") + list("𝄞💩")
+    parts = []
+    for _ in range(6000):
+        if rng.random() < 0.3:   # plant a needle with random per-code-point upper-casing
+            n = needles[int(rng.integers(0, len(needles)))]
+            parts.append("".join((c.upper() if (rng.random() < 0.5 and len(c.upper()) == 1) else c) for c in n))
+        parts.append("".join(cps[int(i)] for i in rng.integers(0, len(cps), size=int(rng.integers(50, 400)))))
+    hay = "".join(parts).encode("utf-8")
+    m = machine(am, needles, cs=1)
+    want = oracle.Machine(needles).find_all(hay, cs=1, lower=lower_dense)
+    assert len(want) > 1500
+    got = m.find_all(hay)
+    assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])
+    assert m.count_matches(hay) == len(want)
+
+
+def test_config5_downscaled_many_needles(am, oracle, torch_cuda):
+    """BASELINE.json config 5 down-scaled: 100 000 needles (6-16 B), 32 MiB haystack in 4 shards with halos;
+    per-shard lists concatenate to the single-shard list; counts all-gathered (here: summed) match."""
+    torch = torch_cuda
+    from alfred_margaret_b200 import sharded, synth
+    needles = synth.random_needles(100000, 72, 6, 16)
+    n = 32 << 20
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    synth.fill_dev(dev.data_ptr(), n, 0, 73)
+    synth.plant_dev(dev.data_ptr(), n, 0, 74, needles)
+    host = dev.cpu().numpy()
+    want = oracle.Machine(needles).find_all(host, threads=8, cap=1 << 20)
+    m = machine(am, needles)
+    halo = m.info()["halo_bytes"]
+    parts = []
+    for r in range(4):
+        w, b, e = sharded.shard_plan(n, halo, 4, r)
+        cnt = m.count_matches_dev(dev.data_ptr() + w, e - w, report_begin=b - w, pos_base=w)
+        out = torch.empty(2 * (cnt + 1), dtype=torch.int64, device="cuda")
+        k = m.find_all_dev(dev.data_ptr() + w, e - w, out.data_ptr(), cnt + 1, report_begin=b - w, pos_base=w)
+        assert k == cnt
+        parts.append(out[: 2 * k].cpu().numpy().view(am.automaton.MATCH_DTYPE))
+    got = np.concatenate(parts)
+    assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])
