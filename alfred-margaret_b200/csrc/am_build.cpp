@@ -222,9 +222,9 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   if (cs == AM_CASE_SENSITIVE) A->halo_bytes = A->max_len > 0 ? A->max_len - 1 : 0;
   else A->halo_bytes = A->max_len_cps > 0 ? 4ull * A->max_len_cps + 4 : 0;
 
-  // ---- 6. dense rows for the shallowest states ---------------------------------------------------------------
+  // ---- 6. dense rows for the shallowest states (generic fallback of ac_step) ---------------------------------
   {
-    uint32_t cap = 16384;  // 16 MiB of rows at most: stays L2-resident (126 MB L2)
+    uint32_t cap = 256;
     A->dense_states = std::min(S, cap);
     A->dense.assign((size_t)A->dense_states * 256, 0);
     for (uint32_t s = 0; s < A->dense_states; s++) {
@@ -232,6 +232,28 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       if (s == 0) { for (int b = 0; b < 256; b++) row[b] = 0; }
       else std::memcpy(row, A->dense.data() + (size_t)A->fail[s] * 256, 256 * sizeof(uint32_t));  // fail(s) < s
       for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) row[A->child_byte[c]] = tagged(A->child_state[c]);
+    }
+  }
+  // ---- 6b. class-compressed failure-resolved automaton (walk kernel) ------------------------------------------
+  {
+    bool used[256] = {false};
+    for (uint8_t cb : A->child_byte) used[cb] = true;
+    uint32_t nc = 1;
+    for (int b = 0; b < 256; b++) A->cls[b] = used[b] ? (uint8_t)(nc++ & 0xFF) : 0;
+    if (nc > 256) {  // all 256 byte values occur: class 0 must still mean "no edge anywhere"; use the identity map
+      for (int b = 0; b < 256; b++) A->cls[b] = (uint8_t)b;
+      nc = 256;
+    }
+    A->num_classes = nc;
+    A->cdfa_shift = 1; while ((1u << A->cdfa_shift) < nc) A->cdfa_shift++;
+    const uint64_t stride = 1ull << A->cdfa_shift;
+    const uint64_t budget_words = (256ull << 20) / 4;                       // 256 MiB of rows at most
+    A->cdfa_states = (uint32_t)std::min<uint64_t>(S, budget_words / stride);
+    A->cdfa.assign((size_t)A->cdfa_states * stride, 0);
+    for (uint32_t s = 0; s < A->cdfa_states; s++) {
+      uint32_t* row = A->cdfa.data() + (size_t)s * stride;
+      if (s != 0) std::memcpy(row, A->cdfa.data() + (size_t)A->fail[s] * stride, stride * sizeof(uint32_t));  // fail(s) < s
+      for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) row[A->cls[A->child_byte[c]]] = tagged(A->child_state[c]);
     }
   }
 

@@ -26,12 +26,15 @@ struct DevAutomaton {
   const uint32_t* chain_count;
   const uint32_t* id_of_rank;
   const uint32_t* len_of_rank;
+  const uint32_t* cdfa;         // class-compressed failure-resolved rows (walk kernel)
+  const uint8_t* cls;           // byte -> class (256 entries)
   const uint16_t* lower1;       // two-stage Char.toLower table
   const int32_t* lower2;
   uint32_t dense_states, edge_mask, jump_mask;
   uint32_t q, qmask, min_len, max_len, rank_bits, num_states, num_needles;
   uint32_t ignore_case, halo;
   uint32_t t2_exact, t2_empty_key;
+  uint32_t cdfa_states, cdfa_shift;
 };
 
 struct ScanArgs {

@@ -86,6 +86,11 @@ struct HostAutomaton {
 
   uint32_t dense_states = 0;                    // rows in `dense`
   std::vector<uint32_t> dense;                  // dense_states * 256, failure-resolved, OUT_FLAG tagged
+  // Class-compressed failure-resolved automaton for the walk kernel: byte -> class (0 = "no needle
+  // contains this byte"), then next = cdfa[state << cdfa_shift | class] for the first cdfa_states states.
+  uint8_t cls[256] = {0};
+  uint32_t num_classes = 1, cdfa_shift = 1, cdfa_states = 0;
+  std::vector<uint32_t> cdfa;
   std::vector<EdgeSlot> edges; uint32_t edge_mask = 0;
   std::vector<JumpSlot> jump; uint32_t jump_mask = 0;
   std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated

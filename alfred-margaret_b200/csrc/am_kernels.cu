@@ -26,8 +26,25 @@ namespace am {
 // =====================================================================================================
 // walk_kernel
 // =====================================================================================================
-constexpr int WALK_THREADS = 128;
+// Every thread walks one text segment through the failure-resolved, class-compressed automaton:
+//   class = cls[byte]                 (256-byte table in shared memory)
+//   next  = row(state)[class]         (rows of the shallowest states are staged into shared memory with a TMA
+//                                      bulk copy; deeper rows come from L2 / HBM through the read-only path)
+// The thread starts max-needle-length - 1 bytes (the halo) before its segment so that its state is exact by
+// the time it reaches the segment, and reports the matches that END inside the segment.
+constexpr int WALK_THREADS = 512;
 constexpr int WALK_STAGE = 1024;
+constexpr int WALK_HOT_BYTES = 88 * 1024;      // hot rows per CTA (2 CTAs per SM)
+
+struct WalkSmem {
+  uint32_t hot[WALK_HOT_BYTES / 4];
+  uint8_t cls[256];
+  KeyStage<WALK_STAGE> stage;
+  unsigned long long red[WALK_THREADS / 32];
+  alignas(8) unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int MODE>
 __device__ __forceinline__ void report_chain(const DevAutomaton& A, const ScanArgs& a, uint32_t tagged,
@@ -48,10 +65,43 @@ __device__ __forceinline__ void report_chain(const DevAutomaton& A, const ScanAr
   }
 }
 
+// One automaton step on byte `b`; `state` untagged, result tagged.
+__device__ __forceinline__ uint32_t walk_step(const DevAutomaton& A, const WalkSmem* sm, uint32_t hot_states, uint32_t state, uint32_t b) {
+  const uint32_t idx = (state << A.cdfa_shift) + sm->cls[b];
+  if (state < hot_states) return sm->hot[idx];
+  if (state < A.cdfa_states) return __ldg(A.cdfa + idx);
+  return ac_step(A, state, b);                             // beyond the row budget (> 256 MiB of rows): goto + failure
+}
+
 template <bool IGNORE_CASE, int MODE>
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs) {
-  __shared__ KeyStage<WALK_STAGE> stage;
-  if (MODE == MODE_EMIT) { stage.init(); __syncthreads(); }
+__global__ void __launch_bounds__(WALK_THREADS, 2) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs, uint32_t hot_states) {
+  extern __shared__ __align__(128) unsigned char walk_smem_raw[];
+  WalkSmem* sm = reinterpret_cast<WalkSmem*>(walk_smem_raw);
+  // ---- stage the class map and the hot rows (TMA bulk copy of the row prefix) -----------------------------
+  const uint32_t hot_bytes = (hot_states << A.cdfa_shift) * 4u;    // multiple of 16: a row is >= 2 words, hot_states is even or rows >= 16 B
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm->mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->mbar)), "r"(hot_bytes + 256u) : "memory");
+    for (uint32_t off = 0; off < hot_bytes; off += 16384) {
+      const uint32_t n = hot_bytes - off < 16384 ? hot_bytes - off : 16384;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->hot) + off)),
+                   "l"(reinterpret_cast<const unsigned char*>(A.cdfa) + off), "r"(n), "r"(smem_u32(&sm->mbar))
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm->cls)),
+                 "l"(A.cls), "r"(256u), "r"(smem_u32(&sm->mbar))
+                 : "memory");
+  }
+  if (MODE == MODE_EMIT) sm->stage.init();
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&sm->mbar)), "r"(0u) : "memory");
+  }
   unsigned long long local_count = 0;
 
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
@@ -72,9 +122,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(DevAutomaton A, Scan
       bool synced = !(IGNORE_CASE && (w > 0 || a.report_begin > 0));
 
       uint64_t v = w + a0; const uint64_t vend = e + a0;
+      uint64_t c = v >> 4;
+      uint4 q4 = __ldg(base16 + c);
       while (v < vend) {
-        const uint64_t c = v >> 4;
-        const uint4 q4 = __ldg(base16 + c);
+        const uint64_t cn = c + 1;
+        uint4 nq = make_uint4(0, 0, 0, 0);
+        if ((cn << 4) < vend) nq = __ldg(base16 + cn);      // next granule, requested before this one is walked
         const uint32_t words[4] = {q4.x, q4.y, q4.z, q4.w};
         const uint32_t jlo = (uint32_t)(v & 15);
         const uint64_t left = vend - (c << 4);
@@ -85,58 +138,61 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(DevAutomaton A, Scan
           const uint32_t byte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
           const uint64_t pos = (c << 4) + j - a0 + 1;  // offset one past this byte
           if (!IGNORE_CASE) {
-            const uint32_t t = ac_step(A, state, byte);
+            const uint32_t t = walk_step(A, sm, hot_states, state, byte);
             state = t & ID_MASK;
-            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &stage);
+            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &sm->stage);
           } else {
             // consumeInput (Automaton.hs:468-480): decode one code point (Utf8.hs:337-350), lower it
             // (Utf8.hs:145-151), feed the bytes of the lowered code point to the byte automaton.
             if (!synced) { if ((byte & 0xC0u) == 0x80u) continue; synced = true; }  // start on a code point boundary
-            bool complete;
-            if (rem == 0) {
-              if (byte < 0xC0u) { cp = byte; complete = true; }
-              else if (byte < 0xE0u) { cp = byte & 0x1Fu; rem = 1; complete = false; }
-              else if (byte < 0xF0u) { cp = byte & 0x0Fu; rem = 2; complete = false; }
-              else { cp = byte & 0x07u; rem = 3; complete = false; }
-            } else {
-              cp = (cp << 6) | (byte & 0x3Fu); rem--; complete = rem == 0;
-            }
-            if (!complete) continue;
-            const uint32_t l = lower_cp(A, cp);
             uint32_t t;
-            if (l < 0x80u) { t = ac_step(A, state, l); }
-            else if (l < 0x800u) {
-              t = ac_step(A, state, 0xC0u | (l >> 6));
-              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
-            } else if (l < 0x10000u) {
-              t = ac_step(A, state, 0xE0u | (l >> 12));
-              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
-              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
+            if (rem == 0 && byte < 0x80u) {               // ASCII fast path: toLowerAscii (Utf8.hs:131-135)
+              t = walk_step(A, sm, hot_states, state, byte + ((byte - 'A' < 26u) ? 0x20u : 0u));
             } else {
-              t = ac_step(A, state, 0xF0u | (l >> 18));
-              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 12) & 0x3Fu));
-              t = ac_step(A, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
-              t = ac_step(A, t & ID_MASK, 0x80u | (l & 0x3Fu));
+              bool complete;
+              if (rem == 0) {
+                if (byte < 0xC0u) { cp = byte; complete = true; }
+                else if (byte < 0xE0u) { cp = byte & 0x1Fu; rem = 1; complete = false; }
+                else if (byte < 0xF0u) { cp = byte & 0x0Fu; rem = 2; complete = false; }
+                else { cp = byte & 0x07u; rem = 3; complete = false; }
+              } else {
+                cp = (cp << 6) | (byte & 0x3Fu); rem--; complete = rem == 0;
+              }
+              if (!complete) continue;
+              const uint32_t l = lower_cp(A, cp);
+              if (l < 0x80u) { t = walk_step(A, sm, hot_states, state, l); }
+              else if (l < 0x800u) {
+                t = walk_step(A, sm, hot_states, state, 0xC0u | (l >> 6));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+              } else if (l < 0x10000u) {
+                t = walk_step(A, sm, hot_states, state, 0xE0u | (l >> 12));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+              } else {
+                t = walk_step(A, sm, hot_states, state, 0xF0u | (l >> 18));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 12) & 0x3Fu));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+              }
             }
             state = t & ID_MASK;
-            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &stage);
+            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &sm->stage);
           }
         }
-        v = (c + 1) << 4;
+        v = cn << 4; c = cn; q4 = nq;
       }
     }
-    if (MODE == MODE_EMIT) stage.flush(a);
+    if (MODE == MODE_EMIT) sm->stage.flush(a);
   }
 
   if (MODE == MODE_COUNT) {
     // CTA reduction, one global atomic per CTA
-    __shared__ unsigned long long red[WALK_THREADS / 32];
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local_count;
+    if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = local_count;
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long s = 0;
-      for (int i = 0; i < WALK_THREADS / 32; i++) s += red[i];
+      for (int i = 0; i < WALK_THREADS / 32; i++) s += sm->red[i];
       if (s) atomicAdd(a.d_count, s);
     }
   }
@@ -186,8 +242,6 @@ struct FilterSmem {
   unsigned long long red[FK_WARPS];
   alignas(8) unsigned long long mbar;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct FilterCtx {
   const uint32_t* base32; uint64_t nwords; uint32_t a0; uint64_t v_begin; uint32_t warp, lane;
@@ -519,6 +573,12 @@ static int sm_count() {
 template <bool IC, int MODE>
 static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   if (a.text_len <= a.report_begin) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(walk_kernel<IC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   const uint64_t span = a.text_len - a.report_begin;
   // segment: long enough to amortise the halo, short enough to fill the GPU
   uint64_t seg = (uint64_t)A.halo * 8; if (seg < 256) seg = 256;
@@ -527,10 +587,13 @@ static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaS
   seg = (seg + 15) & ~15ull;
   const uint64_t nseg = (span + seg - 1) / seg;
   uint64_t blocks = (nseg + WALK_THREADS - 1) / WALK_THREADS;
-  const uint64_t max_blocks = (uint64_t)sm_count() * 16;
+  const uint64_t max_blocks = (uint64_t)sm_count() * 2;
   if (blocks > max_blocks) blocks = max_blocks;
+  // rows staged in shared memory: as many of the shallowest (BFS-first) states as fit, a whole number of 16-byte units
+  uint32_t hot = (uint32_t)std::min<uint64_t>(A.cdfa_states, (uint64_t)WALK_HOT_BYTES / (4ull << A.cdfa_shift));
+  if (A.cdfa_shift == 1) hot &= ~1u;
   g_kernel_launches++;
-  walk_kernel<IC, MODE><<<(unsigned)blocks, WALK_THREADS, 0, st>>>(A, a, seg, nseg);
+  walk_kernel<IC, MODE><<<(unsigned)blocks, WALK_THREADS, sizeof(WalkSmem), st>>>(A, a, seg, nseg, hot);
   return cudaGetLastError();
 }
 

@@ -301,3 +301,27 @@ def test_config5_downscaled_many_needles(am, oracle, torch_cuda):
         parts.append(out[: 2 * k].cpu().numpy().view(am.automaton.MATCH_DTYPE))
     got = np.concatenate(parts)
     assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])
+
+
+def test_large_positions_and_kernel_choice(am, oracle, torch_cuda):
+    """pos_base beyond 2^32 (sort keys use bits(len + pos_base) + rank bits); kernel heuristic for big needle sets."""
+    torch = torch_cuda
+    from alfred_margaret_b200 import synth
+    needles = synth.random_needles(500, 5, 3, 8, b"abc")
+    n = 1 << 20
+    host = synth.fill_host(0, n, 6, b"abc")
+    want = oracle.Machine(needles).find_all(host, cap=1 << 20)
+    dev = torch.from_numpy(host).cuda()
+    base = (1 << 41) + 12345
+    for kind in (0, 1):
+        m = machine(am, needles, force_kernel=kind)
+        out = torch.empty(2 * (len(want) + 1), dtype=torch.int64, device="cuda")
+        k = m.find_all_dev(dev.data_ptr(), n, out.data_ptr(), len(want) + 1, pos_base=base)
+        rec = out[: 2 * k].cpu().numpy().view(am.automaton.MATCH_DTYPE)
+        assert k == len(want) and np.array_equal(rec["end_pos"].astype(np.int64) - base, want["pos"]) and np.array_equal(rec["needle_id"].astype(np.int64), want["value"])
+    assert machine(am, synth.random_needles(1000, 42)).info()["kernel_kind"] == 2
+    big = machine(am, synth.random_needles(40000, 43, 6, 12))
+    assert big.info()["kernel_kind"] == 1                      # too many distinct q-grams for the shared-memory bitmap
+    forced = machine(am, synth.random_needles(40000, 43, 6, 12), force_kernel=2)
+    hay = synth.fill_host(0, 1 << 20, 44)
+    assert as_pairs(forced.find_all(hay)) == as_pairs(big.find_all(hay))
