@@ -136,7 +136,27 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
     if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
     cudaEventRecord(g_ev0, st);
   }
-  e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
+  if (a->kernel_kind == 2 && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
+    // runLower on the filter kernel: scan a lowered copy of the text (same byte offsets).  If the text holds a
+    // code point whose lowering changes its UTF-8 length, fall back to the exact per-code-point walk.
+    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(t.dev_text) & 15);
+    int rc = ws->need_aux(t.text_len + 64, 0);
+    if (rc) return rc;
+    unsigned int* d_exc = reinterpret_cast<unsigned int*>(ws->d_scalars + 16);
+    e = cudaMemsetAsync(d_exc, 0, 4, st);
+    if (e == cudaSuccess) e = launch_lower(a->dev, sa.text, t.text_len, ws->aux_a + a0, d_exc, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 16, d_exc, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "lowering pass");
+    if (*reinterpret_cast<unsigned int*>(ws->h_scalars + 16) == 0) {
+      sa.text = ws->aux_a + a0;
+      e = launch_filter(a->dev, sa, mode, st);
+    } else {
+      e = launch_walk(a->dev, sa, mode, st);
+    }
+  } else {
+    e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
+  }
   if (prof) { cudaEventRecord(g_ev1, st); g_ev_valid = true; }
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return AM_OK;
@@ -236,7 +256,7 @@ int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_low
   // The q-gram filter keeps 16 private 64 Ki-bit copies of its bitmap in shared memory; beyond a few
   // thousand distinct q-grams its false-positive rate (keys / 65 536) swamps the second level, and the
   // per-segment walk is the better kernel.  force_kernel = 2 overrides the heuristic.
-  const bool filter_ok = cs == AM_CASE_SENSITIVE && H.q > 0;
+  const bool filter_ok = H.q > 0;   // IgnoreCase runs the filter on a lowered copy of the text (launch_scan)
   const bool filter_good = filter_ok && H.filter_keys <= 16384;   // measured: 10 k needles 715 GB/s (filter) vs 445 GB/s (walk)
   a->kernel_kind = (force == 2 && filter_ok) || (force != 1 && filter_good) ? 2 : 1;
   if (force == 2 && a->kernel_kind != 2) { delete a; return fail(AM_E_UNSUPPORTED, "filter kernel not applicable to this needle set"); }

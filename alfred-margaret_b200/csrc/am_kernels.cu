@@ -544,6 +544,86 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
 }
 
 // =====================================================================================================
+// lower_kernel -- IgnoreCase front end of the filter kernel
+// =====================================================================================================
+// `runLower` (Automaton.hs:551-553) lower-cases every haystack code point on the fly (Utf8.lowerCodePoint,
+// Utf8.hs:145-151) and matches the lowered code points against needles the caller lowered.  When a lowering
+// keeps the UTF-8 length of its code point -- true for all but a handful of code points (K U+212A, Å U+212B,
+// ẞ U+1E9E, İ U+0130, Ⱥ, Ⱦ, ...) -- the lowered text has the same byte offsets as the original, so the scan
+// can run the CaseSensitive kernels on a lowered COPY of the text.  This kernel writes that copy: one thread
+// per 16-byte granule, SWAR for all-ASCII granules, decode -> table -> re-encode otherwise.  A code point
+// whose lowering changes length is overwritten with 0xFF bytes (never part of a valid UTF-8 needle) and
+// counted; the host then falls back to the exact per-code-point walk kernel for that text.
+__global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_t* text, uint64_t text_len, uint8_t* out /* same misalignment as text */,
+                                                    unsigned int* exceptions) {
+  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(text);
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* in16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  uint4* out16 = reinterpret_cast<uint4*>(out - a0);
+  const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in16);
+  const uint64_t nvec = (a0 + text_len + 15) >> 4;
+  for (uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < nvec; gi += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 q = ld_stream_v4(in16 + gi);
+    if (((q.x | q.y | q.z | q.w) & 0x80808080u) == 0) {
+      // toLowerAscii (Utf8.hs:131-135) on 16 bytes at once: bit 7 of (c + 0x3f) & ~(c + 0x25) marks 'A'..'Z'
+      uint4 r;
+      r.x = q.x | ((((q.x + 0x3f3f3f3fu) & ~(q.x + 0x25252525u)) & 0x80808080u) >> 2);
+      r.y = q.y | ((((q.y + 0x3f3f3f3fu) & ~(q.y + 0x25252525u)) & 0x80808080u) >> 2);
+      r.z = q.z | ((((q.z + 0x3f3f3f3fu) & ~(q.z + 0x25252525u)) & 0x80808080u) >> 2);
+      r.w = q.w | ((((q.w + 0x3f3f3f3fu) & ~(q.w + 0x25252525u)) & 0x80808080u) >> 2);
+      out16[gi] = r;
+      continue;
+    }
+    // general path: bytes [-4, 20) of the granule in a local window, every code point that overlaps [0, 16)
+    // is decoded (decodeN, Utf8.hs:344-350), lowered, re-encoded (unicode2utf8, :154-160)
+    uint8_t win[24], res[16];
+    const uint32_t prev = gi > 0 ? __ldg(in32 + gi * 4 - 1) : 0u;
+    const uint32_t next = gi + 1 < nvec ? __ldg(in32 + (gi + 1) * 4) : 0u;
+    const uint32_t wds[6] = {prev, q.x, q.y, q.z, q.w, next};
+#pragma unroll
+    for (int i = 0; i < 24; i++) win[i] = (uint8_t)(wds[i >> 2] >> (8 * (i & 3)));
+#pragma unroll
+    for (int i = 0; i < 16; i++) res[i] = win[4 + i];
+    const long long vbase = (long long)(gi << 4) - 4;        // virtual index of win[0]
+    const long long lo = (long long)a0, hi = (long long)(a0 + text_len);
+    for (int p = 1; p < 20; p++) {                            // p = index in win of a potential lead byte
+      const long long v = vbase + p;
+      if (v < lo || v >= hi) continue;
+      const uint32_t b0 = win[p];
+      if ((b0 & 0xC0u) == 0x80u) continue;                    // continuation byte: handled with its lead
+      uint32_t len, cp;
+      if (b0 < 0x80u) { len = 1; cp = b0; }
+      else if (b0 < 0xE0u) { len = 2; cp = b0 & 0x1Fu; }
+      else if (b0 < 0xF0u) { len = 3; cp = b0 & 0x0Fu; }
+      else { len = 4; cp = b0 & 0x07u; }
+      if (p + (int)len <= 4) continue;                        // ends before the granule
+      if (p >= 20) break;
+      bool whole = v + len <= hi && p + (int)len <= 24;       // truncated at the text end / window: copy through
+      for (uint32_t k = 1; k < len && whole; k++) cp = (cp << 6) | (win[p + k] & 0x3Fu);
+      if (!whole) continue;
+      const uint32_t l = lower_cp(A, cp);
+      uint8_t enc[4]; uint32_t elen;
+      if (l < 0x80u) { enc[0] = (uint8_t)l; elen = 1; }
+      else if (l < 0x800u) { enc[0] = 0xC0u | (l >> 6); enc[1] = 0x80u | (l & 0x3Fu); elen = 2; }
+      else if (l < 0x10000u) { enc[0] = 0xE0u | (l >> 12); enc[1] = 0x80u | ((l >> 6) & 0x3Fu); enc[2] = 0x80u | (l & 0x3Fu); elen = 3; }
+      else { enc[0] = 0xF0u | (l >> 18); enc[1] = 0x80u | ((l >> 12) & 0x3Fu); enc[2] = 0x80u | ((l >> 6) & 0x3Fu); enc[3] = 0x80u | (l & 0x3Fu); elen = 4; }
+      const bool same = elen == len;
+      if (!same && p >= 4 && p < 20) atomicAdd(exceptions, 1u);   // counted once, by the granule that holds the lead byte
+      for (uint32_t k = 0; k < len; k++) {
+        const int qi = p + (int)k - 4;
+        if (qi >= 0 && qi < 16) res[qi] = same ? enc[k] : (uint8_t)0xFF;
+      }
+    }
+    uint4 r;
+    r.x = res[0] | (res[1] << 8) | (res[2] << 16) | ((uint32_t)res[3] << 24);
+    r.y = res[4] | (res[5] << 8) | (res[6] << 16) | ((uint32_t)res[7] << 24);
+    r.z = res[8] | (res[9] << 8) | (res[10] << 16) | ((uint32_t)res[11] << 24);
+    r.w = res[12] | (res[13] << 8) | (res[14] << 16) | ((uint32_t)res[15] << 24);
+    out16[gi] = r;
+  }
+}
+
+// =====================================================================================================
 // key -> am_match
 // =====================================================================================================
 __global__ void unpack_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out) {
@@ -644,6 +724,15 @@ cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cu
   if (mode == MODE_COUNT) return launch_filter_m<MODE_COUNT>(A, a, st);
   if (mode == MODE_ANY) return launch_filter_m<MODE_ANY>(A, a, st);
   return launch_filter_m<MODE_EMIT>(A, a, st);
+}
+
+cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, cudaStream_t st) {
+  if (text_len == 0) return cudaSuccess;
+  const uint64_t nvec = ((reinterpret_cast<uintptr_t>(text) & 15) + text_len + 15) >> 4;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((nvec + 255) / 256, (uint64_t)sm_count() * 16);
+  g_kernel_launches++;
+  lower_kernel<<<blocks, 256, 0, st>>>(A, text, text_len, out, exceptions);
+  return cudaGetLastError();
 }
 
 size_t sort_temp_bytes(uint64_t n, int end_bit) {

@@ -99,13 +99,16 @@ def test_random_case_sensitive(am, oracle, kind):
         assert gpu_pairs(m, am.utf8.Text(buf, pad, len(hb))) == want
 
 
-def test_random_ignore_case(am, oracle, lower_dense):
-    rng = np.random.default_rng(200)
+@pytest.mark.parametrize("kind", [0, 1])
+def test_random_ignore_case(am, oracle, lower_dense, kind):
+    """kind 0: filter kernel on a lowered copy of the text (falls back to the walk when a code point changes
+    length under lowering); kind 1: the per-code-point walk kernel."""
+    rng = np.random.default_rng(200 + kind)
     for it in range(150):
         needles, hay = needles_haystack(rng, big=60)
         hb = hay.encode("utf-8")
         ln = [am.utf8.lower_utf8(n) for n in needles]
-        m = machine(am, ln, cs=1)
+        m = machine(am, ln, cs=1, force_kernel=kind)
         want = as_pairs(oracle.Machine(ln).find_all(hb, cs=1, lower=lower_dense))
         assert gpu_pairs(m, hb) == want, (needles, hay)
         assert m.count_matches(hb) == len(want)
@@ -247,6 +250,26 @@ def test_golden_splitter(am, golden):
     # overlapping separators are ignored left to right (stepAccum, Splitter.hs:158-170)
     assert S.split(S.build("aa"), "aaaaa") == [b"", b"", b"a"]
     assert S.split(S.build("x"), "") == [b""]
+
+
+def test_ignore_case_length_preserving_text(am, oracle, lower_dense):
+    """Mixed-case text whose lowerings all keep their UTF-8 length (ASCII, Latin-1, Greek, Cyrillic, 4-byte
+    code points, multi-byte code points straddling 16-byte granules): the filter kernel's fast IgnoreCase path."""
+    rng = np.random.default_rng(77)
+    cps = list("abcdefghijABCDEFGHIJ .,") * 3 + list("éÉöÖßåÅяЯжЖωΩλΛ") + list("𝄞💩€") + list("ǳǲǱ")
+    needles = sorted({"".join(str(c).lower() for c in rng.choice(cps, size=int(rng.integers(2, 7)))) for _ in range(400)})
+    needles = [n for n in needles if n.strip()]
+    hay = "".join(rng.choice(cps, size=300000)).encode("utf-8")
+    ln = [am.utf8.lower_utf8(n) for n in needles]
+    want = oracle.Machine(ln).find_all(hay, cs=1, lower=lower_dense, cap=1 << 20)
+    assert len(want) > 10000
+    for kind in (0, 1):
+        m = machine(am, ln, cs=1, force_kernel=kind)
+        for off in (0, 3):                                   # unaligned slices too
+            buf = np.frombuffer(b"\xc3" * off + hay, dtype=np.uint8)
+            got = m.find_all(am.utf8.Text(buf, off, len(hay)))
+            assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (kind, off)
+        assert m.count_matches(hay) == len(want)
 
 
 def test_config3_downscaled_ignore_case(am, oracle, lower_dense):
