@@ -348,3 +348,35 @@ def test_large_positions_and_kernel_choice(am, oracle, torch_cuda):
     forced = machine(am, synth.random_needles(40000, 43, 6, 12), force_kernel=2)
     hay = synth.fill_host(0, 1 << 20, 44)
     assert as_pairs(forced.find_all(hay)) == as_pairs(big.find_all(hay))
+
+
+def test_launch_span_boundary(am, oracle, torch_cuda):
+    """Texts longer than one filter-kernel launch span (2^31 bytes): matches around the launch boundary equal the
+    oracle's, and the total equals the sum over shards cut elsewhere (size-independent consistency property)."""
+    torch = torch_cuda
+    from alfred_margaret_b200 import sharded, synth
+    needles = synth.random_needles(1000, 42)
+    n = (1 << 31) + (96 << 20) + 7
+    dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    synth.fill_dev(dev.data_ptr(), n, 0, 43)
+    synth.plant_dev(dev.data_ptr(), n, 0, 44, needles)
+    m = machine(am, needles)
+    total = m.count_matches_dev(dev.data_ptr(), n)
+    out = torch.empty(2 * (total + 1), dtype=torch.int64, device="cuda")
+    assert m.find_all_dev(dev.data_ptr(), n, out.data_ptr(), total + 1) == total
+    rec = out[: 2 * total].cpu().numpy().view(am.automaton.MATCH_DTYPE)
+    assert np.all(np.diff(rec["end_pos"].astype(np.int64)) >= 0)                  # sortedness at full size
+    # window of 2 MiB around the 2^31 launch boundary vs the oracle
+    lo, hi = (1 << 31) - (1 << 20), (1 << 31) + (1 << 20)
+    window = dev[lo:hi].cpu().numpy()
+    want = oracle.Machine(needles).find_all(window, cap=1 << 16)
+    sel = rec[(rec["end_pos"] > lo + 16) & (rec["end_pos"] <= hi)]
+    want = want[want["pos"] > 16]
+    assert len(sel) == len(want) and np.array_equal(sel["end_pos"].astype(np.int64) - lo, want["pos"]) and np.array_equal(sel["needle_id"].astype(np.int64), want["value"])
+    # shard sums (3 shards, cuts not at the launch boundary)
+    halo = m.info()["halo_bytes"]
+    s = 0
+    for r in range(3):
+        w, b, e = sharded.shard_plan(n, halo, 3, r)
+        s += m.count_matches_dev(dev.data_ptr() + w, e - w, report_begin=b - w, pos_base=w)
+    assert s == total
