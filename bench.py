@@ -96,6 +96,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm can really use: the affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def make_needles(n):
     from alfred_margaret_b200 import synth
     return synth.random_needles(n, SEED_NEEDLES)
@@ -109,7 +124,7 @@ def run_reference(args):
     import numpy as np
     import am_oracle_py as oracle
     from alfred_margaret_b200 import synth
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     needles = make_needles(args.needles)
     m = oracle.Machine(needles)
     # bounded sample of the C2 haystack: ~0.025 GB/s per core on this needle set => aim at ~1-2 s per step
@@ -204,7 +219,6 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = L.am_profile_kernel_launches() - launches0
-    clocks = sampler.stop()
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -234,6 +248,7 @@ def run_ours(args):
     f1.record()
     barrier()
     wall_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+    clocks = sampler.stop()   # sampled across both timed regions (device-resident steps and end-to-end steps)
     e2e_ms = torch.tensor([max(f0.elapsed_time(f1) / args.steps, 0.0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)

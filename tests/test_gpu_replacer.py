@@ -82,3 +82,24 @@ def test_config4_downscaled(am, oracle):
     got = am.replacer.run(r, hay)
     assert got == want
     assert r.last_passes == o.passes
+
+
+def test_config4_idempotence_at_scale(am):
+    """BASELINE.json config 4 shape at 256 MiB (size-independent properties): with non-empty upper-case
+    replacements no replacement can create or join a lower-case needle, so the result contains no needle and
+    running the replacer again is the identity; lengths add up."""
+    import numpy as np
+    from alfred_margaret_b200 import synth
+    rng = np.random.default_rng(64)
+    needles = synth.random_needles(5000, 62, 5, 16)
+    repls = [bytes(rng.integers(ord("A"), ord("Z") + 1, size=int(rng.integers(1, 25)), dtype=np.uint8)) for _ in needles]
+    hay = synth.fill_host(0, 256 << 20, 63)
+    synth.plant_host(hay, 0, 64, needles[:64])
+    r = am.replacer.build(0, list(zip(needles, repls)))
+    out = am.replacer.run(r, hay)
+    assert 40 <= r.last_passes <= 5001
+    s = am.searcher.build(0, needles)
+    assert am.searcher.contains_any(s, out) is False
+    again = am.replacer.run(r, out)
+    assert again == out and r.last_passes == 1
+    assert am.replacer.run_with_limit(r, len(out) - 1, hay) is None and am.replacer.run_with_limit(r, len(out) + (1 << 20), hay) == out
