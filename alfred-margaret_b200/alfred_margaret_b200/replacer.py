@@ -83,7 +83,8 @@ def run_with_limit(r: Replacer, max_length: int, text) -> Optional[bytes]:
     r.last_passes = _ffi.lib().am_replacer_last_passes()
     if exceeded.value:
         return None
-    res = C.string_at(out.value, out_len.value) if out_len.value else b""
+    n = out_len.value
+    res = bytes(memoryview((C.c_char * n).from_address(out.value))) if n else b""   # (string_at takes a C int: no > 2 GiB)
     _ffi.lib().am_free(out)
     return res
 

@@ -120,6 +120,34 @@ __global__ void gather_kept_kernel(const uint64_t* start, const uint64_t* end, c
 // matches that intersect it and copies the gaps between them, shifted by the prefix sum of the deltas.
 // The CTA that owns a match's first byte (or, for an empty match, its position) writes the replacement.
 constexpr int SPLICE_TILE = 1 << 16;
+
+// CTA-cooperative copy of n bytes with arbitrary relative misalignment: 16-byte aligned stores, the source is
+// read as aligned 32-bit words and re-aligned with funnel shifts.
+__device__ __forceinline__ void splice_copy(uint8_t* d, const uint8_t* s, uint64_t n) {
+  // head: bytes until d is 16-byte aligned
+  uint64_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+  if (head > n) head = n;
+  for (uint64_t x = threadIdx.x; x < head; x += blockDim.x) d[x] = s[x];
+  d += head; s += head; n -= head;
+  const uint64_t nvec = n >> 4;
+  const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - r);   // aligned words; word i covers source bytes [4i - r, 4i - r + 4)
+  uint4* dv = reinterpret_cast<uint4*>(d);
+  if (r == 0) {
+    for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint32_t* p = sw + i * 4;
+      dv[i] = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    }
+  } else {
+    const uint32_t sh = r * 8;
+    for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+      const uint32_t* p = sw + i * 4;
+      const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+      dv[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+  }
+  for (uint64_t x = (nvec << 4) + threadIdx.x; x < n; x += blockDim.x) d[x] = s[x];   // tail
+}
 __global__ void __launch_bounds__(256) splice_kernel(const uint8_t* src, uint64_t src_len, uint8_t* dst, const uint64_t* k_start, const uint64_t* k_end,
                                                      const long long* k_shift /*exclusive prefix of deltas*/, uint64_t K, const uint8_t* repl, uint32_t repl_len,
                                                      long long total_shift) {
@@ -138,7 +166,7 @@ __global__ void __launch_bounds__(256) splice_kernel(const uint8_t* src, uint64_
     const uint64_t gap_end = have ? k_start[k] : t1;
     if (gap_end > cur) {                                    // copy source [cur, gap_end)
       const long long shift = k < K ? k_shift[k] : total_shift;
-      for (uint64_t x = cur + threadIdx.x; x < gap_end; x += blockDim.x) dst[(long long)x + shift] = src[x];
+      splice_copy(dst + ((long long)cur + shift), src + cur, gap_end - cur);
     }
     if (!have) break;
     const long long at = (long long)k_start[k] + k_shift[k];
