@@ -243,8 +243,12 @@ struct FilterSmem {
   alignas(8) unsigned long long mbar;
 };
 
+// Context of the rare out-of-line work (survivor walk, flushes); everything in it is recomputed from kernel
+// parameters and the thread index where it is used, so it costs the hot loop no registers.
 struct FilterCtx {
-  const uint32_t* base32; uint64_t nwords; uint32_t a0; uint64_t v_begin; uint32_t warp, lane;
+  uint64_t v_begin; uint32_t a0, warp, lane;
+  __device__ __forceinline__ FilterCtx(const ScanArgs& a, uint64_t vb)
+      : v_begin(vb), a0((uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15)), warp(threadIdx.x >> 5), lane(threadIdx.x & 31) {}
 };
 
 template <int MODE>
@@ -432,12 +436,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
   }
 
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
-  FilterCtx c;
-  c.a0 = (uint32_t)(addr0 & 15);
-  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - c.a0);
-  c.base32 = reinterpret_cast<const uint32_t*>(base16);
-  const uint64_t nvec = (c.a0 + a.text_len + 15) >> 4;    // 16-byte granules overlapping the text
-  c.nwords = nvec * 4; c.v_begin = v_begin; c.warp = warp; c.lane = lane;
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  const uint32_t* base32 = reinterpret_cast<const uint32_t*>(base16);
+  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text
   const uint32_t filt_lane = smem_u32(sm->filter) + ((lane & (FK_COPIES - 1u)) << 2);   // this lane's private copy (bank)
   uint32_t* win = sm->window[warp];
   const uint32_t win_s = smem_u32(win), t2_s = smem_u32(sm->t2);
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
     A = zero4; B = zero4; tail = 0;
     if (g + lane < nvec) A = ld_stream_v4(base16 + g + lane);
     if (g + 32 + lane < nvec) B = ld_stream_v4(base16 + g + 32 + lane);
-    if (lane == 0 && g + 64 < nvec) tail = __ldg(c.base32 + (g + 64) * 4);
+    if (lane == 0 && g + 64 < nvec) tail = __ldg(base32 + (g + 64) * 4);
   };
   uint4 cA = zero4, cB = zero4;
   uint32_t tail_cur = 0;
@@ -477,7 +479,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base16 + pv), "r"((uint32_t)FK_CHUNK) : "memory");
     }
 #endif
-    const uint4* pn = pl + 64;                            // this lane's granule of the NEXT pair
 #pragma unroll 1
     for (int pair = 0; pair < FK_PAIRS; pair++) {
       // request the next pair (same chunk, or the first pair of this warp's chunk in the CTA's next tile)
@@ -485,13 +486,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
       uint32_t tail_next = 0;
       const bool same = pair + 1 < FK_PAIRS;
       if (interior) {
-        if (!same) pn = pl + tile_stride_granules;
         if (same || has_next) {
+          const uint4* pn = same ? pl + 64 * (pair + 1) : pl + tile_stride_granules;   // this lane's granule of the NEXT pair
           nA = ld_stream_v4(pn);
           nB = ld_stream_v4(pn + 32);
           if (lane == 0) tail_next = __ldg(reinterpret_cast<const uint32_t*>(pn + 64));
         }
-        pn += 64;
       } else if (same || has_next) {
         load_pair_guarded(pair_granule(same ? tile : tile + gridDim.x, same ? pair + 1 : 0), nA, nB, tail_next);
       }
@@ -521,14 +521,14 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
 #endif
           const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
           if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
-          else fk_deep_verify<MODE>(A, a, sm, c, pair_rel + o, g, local_count);   // queue full: verify in place
+          else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), pair_rel + o, g, local_count);   // queue full: verify in place
         }
       }
-      fk_drain<MODE>(A, a, sm, c, local_count, 32);       // only when a full round of survivors waits
+      fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, 32);       // only when a full round of survivors waits
       cA = nA; cB = nB; tail_cur = tail_next;
     }
   }
-  fk_drain<MODE>(A, a, sm, c, local_count, 1);
+  fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, 1);
   if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
 
   if (MODE == MODE_COUNT) {
