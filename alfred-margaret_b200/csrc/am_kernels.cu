@@ -32,16 +32,24 @@ namespace am {
 //                                      bulk copy; deeper rows come from L2 / HBM through the read-only path)
 // The thread starts max-needle-length - 1 bytes (the halo) before its segment so that its state is exact by
 // the time it reaches the segment, and reports the matches that END inside the segment.
-constexpr int WALK_THREADS = 512;
+// A warp step costs the latency of its SLOWEST lane, so one row lookup that leaves shared memory (L2: ~700
+// cycles) stalls 32 lanes: the fraction of lookups served from shared memory matters more than occupancy.
+// Hence one CTA of 1024 threads per SM with as many hot rows as fit (ncu: with 88 KiB of rows per CTA 86 % of the
+// warp steps on C2 waited on L2).
+// For larger automata (hot set >> shared memory) the opposite holds: L1 capacity for the row lookups and
+// two CTAs per SM win (measured: 100 k needles 214 vs 112 GB/s).  The launcher picks per automaton.
+constexpr int WALK_THREADS = 1024;             // upper bound of the block size (launch bounds)
 constexpr int WALK_STAGE = 1024;
-constexpr int WALK_HOT_BYTES = 88 * 1024;      // hot rows per CTA (2 CTAs per SM)
+constexpr int WALK_HOT_BYTES_BIG = 208 * 1024; // hot rows, 1 CTA of 1024 threads per SM (small automata)
+constexpr int WALK_HOT_BYTES_SMALL = 88 * 1024;// hot rows, 2 CTAs of 512 threads per SM (large automata)
+constexpr uint64_t WALK_SMALL_AUTOMATON_BYTES = 2ull << 20;   // all rows <= 2 MiB => the big-hot-set configuration
 
 struct WalkSmem {
-  uint32_t hot[WALK_HOT_BYTES / 4];
   uint8_t cls[256];
   KeyStage<WALK_STAGE> stage;
   unsigned long long red[WALK_THREADS / 32];
   alignas(8) unsigned long long mbar;
+  alignas(16) uint32_t hot[1];                 // hot rows follow (dynamic shared memory)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,7 +82,7 @@ __device__ __forceinline__ uint32_t walk_step(const DevAutomaton& A, const WalkS
 }
 
 template <bool IGNORE_CASE, int MODE>
-__global__ void __launch_bounds__(WALK_THREADS, 2) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs, uint32_t hot_states) {
+__global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs, uint32_t hot_states) {
   extern __shared__ __align__(128) unsigned char walk_smem_raw[];
   WalkSmem* sm = reinterpret_cast<WalkSmem*>(walk_smem_raw);
   // ---- stage the class map and the hot rows (TMA bulk copy of the row prefix) -----------------------------
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(WALK_THREADS, 2) walk_kernel(DevAutomaton A, S
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long s = 0;
-      for (int i = 0; i < WALK_THREADS / 32; i++) s += sm->red[i];
+      for (unsigned i = 0; i < blockDim.x / 32; i++) s += sm->red[i];
       if (s) atomicAdd(a.d_count, s);
     }
   }
@@ -655,25 +663,30 @@ static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaS
   if (a.text_len <= a.report_begin) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(walk_kernel<IC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem));
+    cudaError_t e = cudaFuncSetAttribute(walk_kernel<IC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WalkSmem) + WALK_HOT_BYTES_BIG));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const uint64_t span = a.text_len - a.report_begin;
+  // small automaton: one big CTA per SM with most rows in shared memory; large: two CTAs, rows mostly via L1/L2
+  const uint64_t row_bytes = 4ull << A.cdfa_shift;
+  const bool small = (uint64_t)A.cdfa_states * row_bytes <= WALK_SMALL_AUTOMATON_BYTES;
+  const int threads = small ? 1024 : 512;
+  const uint32_t hot_budget = small ? WALK_HOT_BYTES_BIG : WALK_HOT_BYTES_SMALL;
   // segment: long enough to amortise the halo, short enough to fill the GPU
   uint64_t seg = (uint64_t)A.halo * 8; if (seg < 256) seg = 256;
   const uint64_t want = (uint64_t)sm_count() * 2048;  // threads resident on the whole GPU
   while (seg > 64 && seg > (uint64_t)A.halo * 2 && (span + seg - 1) / seg < want) seg >>= 1;
   seg = (seg + 15) & ~15ull;
   const uint64_t nseg = (span + seg - 1) / seg;
-  uint64_t blocks = (nseg + WALK_THREADS - 1) / WALK_THREADS;
-  const uint64_t max_blocks = (uint64_t)sm_count() * 2;
+  uint64_t blocks = (nseg + threads - 1) / threads;
+  const uint64_t max_blocks = (uint64_t)sm_count() * (small ? 1 : 2);
   if (blocks > max_blocks) blocks = max_blocks;
   // rows staged in shared memory: as many of the shallowest (BFS-first) states as fit, a whole number of 16-byte units
-  uint32_t hot = (uint32_t)std::min<uint64_t>(A.cdfa_states, (uint64_t)WALK_HOT_BYTES / (4ull << A.cdfa_shift));
+  uint32_t hot = (uint32_t)std::min<uint64_t>(A.cdfa_states, (uint64_t)hot_budget / row_bytes);
   if (A.cdfa_shift == 1) hot &= ~1u;
   g_kernel_launches++;
-  walk_kernel<IC, MODE><<<(unsigned)blocks, WALK_THREADS, sizeof(WalkSmem), st>>>(A, a, seg, nseg, hot);
+  walk_kernel<IC, MODE><<<(unsigned)blocks, threads, sizeof(WalkSmem) + hot_budget, st>>>(A, a, seg, nseg, hot);
   return cudaGetLastError();
 }
 

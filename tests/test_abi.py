@@ -129,3 +129,17 @@ def test_synth_host_generator():
     assert np.array_equal(part, full[8000:17000])                              # shard-consistent planting
     planted = sum(full.tobytes().count(n) for n in needles)
     assert planted >= 9
+
+
+def test_benchmark_file_format(golden, tmp_path):
+    """The reference harness's file format (benchmark/haskell/app/Main.hs:26-40): needles, blank line, haystack."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ac_bench", os.path.join(ROOT, "alfred-margaret_b200", "tools", "ac_bench.py"))
+    ac = importlib.util.module_from_spec(spec); spec.loader.exec_module(ac)
+    v = golden["example_file"]
+    p = tmp_path / "example.txt"
+    p.write_bytes(("\n".join(v["needles"]) + "\n\n" + v["haystack"]).encode("utf-8"))
+    needles, hay = ac.read_needle_haystack_file(str(p))
+    assert needles == [n.encode() for n in v["needles"]] and hay == v["haystack"].encode("utf-8")
+    p.write_bytes(b"a\nb")
+    assert ac.read_needle_haystack_file(str(p)) == ([b"a", b"b"], b"")

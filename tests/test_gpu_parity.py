@@ -380,3 +380,18 @@ def test_launch_span_boundary(am, oracle, torch_cuda):
         w, b, e = sharded.shard_plan(n, halo, 3, r)
         s += m.count_matches_dev(dev.data_ptr() + w, e - w, report_begin=b - w, pos_base=w)
     assert s == total
+
+
+def test_ac_bench_protocol(am, golden, tmp_path, capsys):
+    """tools/ac_bench.py speaks the reference harness's protocol (5 timings on stdout, count on stderr)."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ac_bench", os.path.join(root, "alfred-margaret_b200", "tools", "ac_bench.py"))
+    ac = importlib.util.module_from_spec(spec); spec.loader.exec_module(ac)
+    v = golden["example_file"]
+    p = tmp_path / "example.txt"
+    p.write_bytes(("\n".join(v["needles"]) + "\n\n" + v["haystack"]).encode("utf-8"))
+    ac.main([str(p)])
+    cap = capsys.readouterr()
+    assert cap.err.strip() == str(v["expected_count"])
+    assert len([x for x in cap.out.strip().split("\t") if x]) == 5
