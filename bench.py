@@ -309,9 +309,33 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _emit_only_json_on_stdout(fn, args):
+    """Exactly ONE line on stdout: libraries (e.g. NCCL's version banner) print to fd 1, so everything else is
+    routed to stderr while the benchmark runs and the JSON line is written to the saved descriptor at the end."""
+    import builtins
+    real = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    orig_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            orig_print(*a, **k)
+
+    builtins.print = capture
+    try:
+        fn(args)
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+    for ln in lines:
+        orig_print(ln, flush=True)
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    _emit_only_json_on_stdout(run_reference if a.impl == "reference" else run_ours, a)
