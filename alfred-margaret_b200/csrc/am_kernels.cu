@@ -81,6 +81,143 @@ __device__ __forceinline__ uint32_t walk_step(const DevAutomaton& A, const WalkS
   return ac_step(A, state, b);                             // beyond the row budget (> 256 MiB of rows): goto + failure
 }
 
+// Incremental decodeN (Utf8.hs:344-350): returns true when `cp` is complete.
+__device__ __forceinline__ bool walk_decode(uint32_t byte, uint32_t& cp, uint32_t& rem) {
+  if (rem == 0) {
+    if (byte < 0xC0u) { cp = byte; return true; }
+    if (byte < 0xE0u) { cp = byte & 0x1Fu; rem = 1; return false; }
+    if (byte < 0xF0u) { cp = byte & 0x0Fu; rem = 2; return false; }
+    cp = byte & 0x07u; rem = 3; return false;
+  }
+  cp = (cp << 6) | (byte & 0x3Fu);
+  return --rem == 0;
+}
+
+// Feed the UTF-8 bytes of one (lowered) code point; returns the tagged state after its last byte.
+__device__ __forceinline__ uint32_t walk_feed_cp(const DevAutomaton& A, const WalkSmem* sm, uint32_t hot_states, uint32_t state, uint32_t l) {
+  uint32_t t;
+  if (l < 0x80u) return walk_step(A, sm, hot_states, state, l);
+  if (l < 0x800u) {
+    t = walk_step(A, sm, hot_states, state, 0xC0u | (l >> 6));
+    return walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+  }
+  if (l < 0x10000u) {
+    t = walk_step(A, sm, hot_states, state, 0xE0u | (l >> 12));
+    t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+    return walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+  }
+  t = walk_step(A, sm, hot_states, state, 0xF0u | (l >> 18));
+  t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 12) & 0x3Fu));
+  t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
+  return walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
+}
+
+// IgnoreCase: consume one text byte of a chain (consumeInput, Automaton.hs:468-480): decode incrementally
+// (Utf8.hs:337-350), lower (Utf8.hs:145-151), feed the bytes of the lowered code point.  Returns false when the
+// byte did not complete a code point (no state change, nothing to report).
+__device__ __forceinline__ bool walk_ic_byte(const DevAutomaton& A, const WalkSmem* sm, uint32_t hot_states, uint32_t byte,
+                                             uint32_t& state, uint32_t& cp, uint32_t& rem, bool& synced, uint32_t& t) {
+  if (!synced) { if ((byte & 0xC0u) == 0x80u) return false; synced = true; }   // start on a code point boundary
+  if (rem == 0 && byte < 0x80u) {                            // ASCII fast path: toLowerAscii (Utf8.hs:131-135)
+    t = walk_step(A, sm, hot_states, state, byte + ((byte - 'A' < 26u) ? 0x20u : 0u));
+  } else {
+    if (!walk_decode(byte, cp, rem)) return false;
+    t = walk_feed_cp(A, sm, hot_states, state, lower_cp(A, cp));
+  }
+  state = t & ID_MASK;
+  return true;
+}
+
+// Walk ONE segment: the matches whose end position lies in (b, e].  General (edge) path.
+template <bool IGNORE_CASE, int MODE>
+__device__ __forceinline__ void walk_one_segment(const DevAutomaton& A, const ScanArgs& a, WalkSmem* sm, uint32_t hot_states, uint64_t seg,
+                                                 uint64_t seg_bytes, uint32_t a0, const uint4* base16, unsigned long long& local_count) {
+  const uint64_t b = a.report_begin + seg * seg_bytes;
+  uint64_t e = b + seg_bytes; if (e > a.text_len) e = a.text_len;
+  const uint64_t w = b > A.halo ? b - A.halo : 0;  // warm-up start: depth(state) <= max needle length
+  uint32_t state = 0;                              // untagged
+  uint32_t cp = 0, rem = 0;                        // incremental UTF-8 decoder (IgnoreCase)
+  bool synced = !(IGNORE_CASE && (w > 0 || a.report_begin > 0));
+  uint64_t v = w + a0; const uint64_t vend = e + a0;
+  uint64_t c = v >> 4;
+  uint4 q4 = __ldg(base16 + c);
+  while (v < vend) {
+    const uint64_t cn = c + 1;
+    uint4 nq = make_uint4(0, 0, 0, 0);
+    if ((cn << 4) < vend) nq = __ldg(base16 + cn);          // next granule, requested before this one is walked
+    const uint32_t words[4] = {q4.x, q4.y, q4.z, q4.w};
+    const uint32_t jlo = (uint32_t)(v & 15);
+    const uint64_t left = vend - (c << 4);
+    const uint32_t jhi = left < 16 ? (uint32_t)left : 16u;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; j++) {
+      if (j < jlo || j >= jhi) continue;
+      const uint32_t byte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      const uint64_t pos = (c << 4) + j - a0 + 1;            // offset one past this byte
+      uint32_t t;
+      if (!IGNORE_CASE) { t = walk_step(A, sm, hot_states, state, byte); state = t & ID_MASK; }
+      else if (!walk_ic_byte(A, sm, hot_states, byte, state, cp, rem, synced, t)) continue;
+      if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &sm->stage);
+    }
+    v = cn << 4; c = cn; q4 = nq;
+  }
+}
+
+// Walk TWO full-length interior segments in lockstep.  A warp step costs the latency of its slowest lane, and for
+// automata whose hot set exceeds shared memory that latency is an L2 round trip; two independent chains per
+// thread put two lookups in flight per lane.  Both segments have the same length and the same alignment, so
+// they share every byte mask; both warm up over the same (16-byte rounded) halo.
+template <bool IGNORE_CASE, int MODE>
+__device__ __forceinline__ void walk_two_segments(const DevAutomaton& A, const ScanArgs& a, WalkSmem* sm, uint32_t hot_states, uint64_t seg,
+                                                  uint64_t seg_bytes, uint32_t halo_al, uint32_t a0, const uint4* base16,
+                                                  unsigned long long& local_count) {
+  const uint64_t b0 = a.report_begin + seg * seg_bytes, b1 = b0 + seg_bytes;
+  const uint64_t w0 = b0 - halo_al, w1 = b1 - halo_al;
+  const uint64_t v0 = w0 + a0;                                // virtual index of chain 0's first byte
+  const uint64_t vend0 = b0 + seg_bytes + a0;
+  const uint64_t c0 = v0 >> 4, c1 = (w1 + a0) >> 4;
+  const uint32_t nsteps = (uint32_t)(((vend0 + 15) >> 4) - c0);
+  const uint32_t r = (uint32_t)(v0 & 15);                     // bytes of the first granule that precede the chains
+  uint32_t s0 = 0, s1 = 0;                                    // untagged states
+  uint32_t cp0 = 0, cp1 = 0, rem0 = 0, rem1 = 0;
+  bool syn0 = !IGNORE_CASE, syn1 = !IGNORE_CASE;              // IgnoreCase chains start on a code point boundary
+  uint4 q0 = __ldg(base16 + c0), q1 = __ldg(base16 + c1);
+  for (uint32_t step = 0; step < nsteps; step++) {
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    if (step + 1 < nsteps) { n0 = __ldg(base16 + c0 + step + 1); n1 = __ldg(base16 + c1 + step + 1); }
+    const uint32_t wa[4] = {q0.x, q0.y, q0.z, q0.w}, wb[4] = {q1.x, q1.y, q1.z, q1.w};
+    const uint32_t jlo = step == 0 ? r : 0u;
+    const uint32_t jhi = step + 1 == nsteps ? (uint32_t)((vend0 - 1) & 15) + 1u : 16u;
+    const uint32_t tbase = step * 16u - r;                    // chain-relative index of byte j = 0 (wraps for j < r; unused there)
+#pragma unroll
+    for (uint32_t j = 0; j < 16; j++) {
+      if (j < jlo || j >= jhi) continue;
+      const uint32_t x0 = (wa[j >> 2] >> (8 * (j & 3))) & 0xFFu, x1 = (wb[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      const bool rep = tbase + j >= halo_al;                  // end position beyond the segment start
+      uint32_t t0 = 0, t1 = 0;
+      bool ok0 = true, ok1 = true;
+      if (!IGNORE_CASE || (syn0 && syn1 && ((rem0 | rem1) == 0) && ((x0 | x1) < 0x80u))) {
+        // both chains take one plain automaton step: issue the two class lookups, then the two row lookups
+        const uint32_t y0 = IGNORE_CASE ? x0 + ((x0 - 'A' < 26u) ? 0x20u : 0u) : x0;
+        const uint32_t y1 = IGNORE_CASE ? x1 + ((x1 - 'A' < 26u) ? 0x20u : 0u) : x1;
+        const uint32_t k0 = sm->cls[y0], k1 = sm->cls[y1];
+        const uint32_t i0 = (s0 << A.cdfa_shift) + k0, i1 = (s1 << A.cdfa_shift) + k1;
+        t0 = s0 < hot_states ? sm->hot[i0] : __ldg(A.cdfa + i0);
+        t1 = s1 < hot_states ? sm->hot[i1] : __ldg(A.cdfa + i1);
+        s0 = t0 & ID_MASK; s1 = t1 & ID_MASK;
+      } else {
+        ok0 = walk_ic_byte(A, sm, hot_states, x0, s0, cp0, rem0, syn0, t0);
+        ok1 = walk_ic_byte(A, sm, hot_states, x1, s1, cp1, rem1, syn1, t1);
+      }
+      if (rep && ((t0 | t1) & OUT_FLAG)) {
+        if (ok0 && (t0 & OUT_FLAG)) report_chain<MODE>(A, a, t0, w0 + tbase + j + 1, local_count, &sm->stage);
+        if (ok1 && (t1 & OUT_FLAG)) report_chain<MODE>(A, a, t1, w1 + tbase + j + 1, local_count, &sm->stage);
+      }
+    }
+    q0 = n0; q1 = n1;
+  }
+}
+
 template <bool IGNORE_CASE, int MODE>
 __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, ScanArgs a, uint64_t seg_bytes, uint64_t num_segs, uint32_t hot_states) {
   extern __shared__ __align__(128) unsigned char walk_smem_raw[];
@@ -115,79 +252,25 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, S
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
   const uint32_t a0 = (uint32_t)(addr0 & 15);
   const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  const uint32_t halo_al = (A.halo + 15u) & ~15u;
+  // the lockstep path indexes the row table directly; beyond an L2-sized table the row lookups are bandwidth-
+  // rather than latency-bound and a second chain only adds pressure (measured: 100 k needles 213 vs 196 GB/s)
+  const bool pairable = A.cdfa_states == A.num_states && ((uint64_t)A.cdfa_states << A.cdfa_shift) * 4 <= (64ull << 20);
+  const uint64_t num_pairs = (num_segs + 1) >> 1;
 
-  for (uint64_t seg0 = (uint64_t)blockIdx.x * blockDim.x; seg0 < num_segs; seg0 += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t seg = seg0 + threadIdx.x;
-    bool live = seg < num_segs;
+  for (uint64_t p0 = (uint64_t)blockIdx.x * blockDim.x; p0 < num_pairs; p0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t pr = p0 + threadIdx.x;
+    bool live = pr < num_pairs;
     if (MODE == MODE_ANY && live && *reinterpret_cast<volatile int*>(a.d_flag)) live = false;
     if (live) {
-      // This thread owns the matches whose end position lies in (b, e].
-      const uint64_t b = a.report_begin + seg * seg_bytes;
-      uint64_t e = b + seg_bytes; if (e > a.text_len) e = a.text_len;
-      uint64_t w = b > A.halo ? b - A.halo : 0;  // warm-up start: depth(state) <= max needle length
-      uint32_t state = 0;                        // untagged
-      uint32_t cp = 0, rem = 0;                  // incremental UTF-8 decoder (IgnoreCase)
-      bool synced = !(IGNORE_CASE && (w > 0 || a.report_begin > 0));
-
-      uint64_t v = w + a0; const uint64_t vend = e + a0;
-      uint64_t c = v >> 4;
-      uint4 q4 = __ldg(base16 + c);
-      while (v < vend) {
-        const uint64_t cn = c + 1;
-        uint4 nq = make_uint4(0, 0, 0, 0);
-        if ((cn << 4) < vend) nq = __ldg(base16 + cn);      // next granule, requested before this one is walked
-        const uint32_t words[4] = {q4.x, q4.y, q4.z, q4.w};
-        const uint32_t jlo = (uint32_t)(v & 15);
-        const uint64_t left = vend - (c << 4);
-        const uint32_t jhi = left < 16 ? (uint32_t)left : 16u;
-#pragma unroll
-        for (uint32_t j = 0; j < 16; j++) {
-          if (j < jlo || j >= jhi) continue;
-          const uint32_t byte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-          const uint64_t pos = (c << 4) + j - a0 + 1;  // offset one past this byte
-          if (!IGNORE_CASE) {
-            const uint32_t t = walk_step(A, sm, hot_states, state, byte);
-            state = t & ID_MASK;
-            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &sm->stage);
-          } else {
-            // consumeInput (Automaton.hs:468-480): decode one code point (Utf8.hs:337-350), lower it
-            // (Utf8.hs:145-151), feed the bytes of the lowered code point to the byte automaton.
-            if (!synced) { if ((byte & 0xC0u) == 0x80u) continue; synced = true; }  // start on a code point boundary
-            uint32_t t;
-            if (rem == 0 && byte < 0x80u) {               // ASCII fast path: toLowerAscii (Utf8.hs:131-135)
-              t = walk_step(A, sm, hot_states, state, byte + ((byte - 'A' < 26u) ? 0x20u : 0u));
-            } else {
-              bool complete;
-              if (rem == 0) {
-                if (byte < 0xC0u) { cp = byte; complete = true; }
-                else if (byte < 0xE0u) { cp = byte & 0x1Fu; rem = 1; complete = false; }
-                else if (byte < 0xF0u) { cp = byte & 0x0Fu; rem = 2; complete = false; }
-                else { cp = byte & 0x07u; rem = 3; complete = false; }
-              } else {
-                cp = (cp << 6) | (byte & 0x3Fu); rem--; complete = rem == 0;
-              }
-              if (!complete) continue;
-              const uint32_t l = lower_cp(A, cp);
-              if (l < 0x80u) { t = walk_step(A, sm, hot_states, state, l); }
-              else if (l < 0x800u) {
-                t = walk_step(A, sm, hot_states, state, 0xC0u | (l >> 6));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
-              } else if (l < 0x10000u) {
-                t = walk_step(A, sm, hot_states, state, 0xE0u | (l >> 12));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
-              } else {
-                t = walk_step(A, sm, hot_states, state, 0xF0u | (l >> 18));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 12) & 0x3Fu));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | ((l >> 6) & 0x3Fu));
-                t = walk_step(A, sm, hot_states, t & ID_MASK, 0x80u | (l & 0x3Fu));
-              }
-            }
-            state = t & ID_MASK;
-            if ((t & OUT_FLAG) && pos > b) report_chain<MODE>(A, a, t, pos, local_count, &sm->stage);
-          }
-        }
-        v = cn << 4; c = cn; q4 = nq;
+      const uint64_t seg = pr * 2;
+      const uint64_t b0 = a.report_begin + seg * seg_bytes;
+      // interior pair: both segments exist with full length and the rounded halo does not reach before the text
+      if (pairable && seg + 1 < num_segs && b0 >= halo_al && b0 + 2 * seg_bytes <= a.text_len) {
+        walk_two_segments<IGNORE_CASE, MODE>(A, a, sm, hot_states, seg, seg_bytes, halo_al, a0, base16, local_count);
+      } else {
+        walk_one_segment<IGNORE_CASE, MODE>(A, a, sm, hot_states, seg, seg_bytes, a0, base16, local_count);
+        if (seg + 1 < num_segs) walk_one_segment<IGNORE_CASE, MODE>(A, a, sm, hot_states, seg + 1, seg_bytes, a0, base16, local_count);
       }
     }
     if (MODE == MODE_EMIT) sm->stage.flush(a);
@@ -675,11 +758,12 @@ static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaS
   const uint32_t hot_budget = small ? WALK_HOT_BYTES_BIG : WALK_HOT_BYTES_SMALL;
   // segment: long enough to amortise the halo, short enough to fill the GPU
   uint64_t seg = (uint64_t)A.halo * 8; if (seg < 256) seg = 256;
-  const uint64_t want = (uint64_t)sm_count() * 2048;  // threads resident on the whole GPU
+  const uint64_t want = (uint64_t)sm_count() * 2048;  // segments wanted: two per resident thread
   while (seg > 64 && seg > (uint64_t)A.halo * 2 && (span + seg - 1) / seg < want) seg >>= 1;
   seg = (seg + 15) & ~15ull;
   const uint64_t nseg = (span + seg - 1) / seg;
-  uint64_t blocks = (nseg + threads - 1) / threads;
+  const uint64_t npairs = (nseg + 1) / 2;              // a thread walks two segments in lockstep
+  uint64_t blocks = (npairs + threads - 1) / threads;
   const uint64_t max_blocks = (uint64_t)sm_count() * (small ? 1 : 2);
   if (blocks > max_blocks) blocks = max_blocks;
   // rows staged in shared memory: as many of the shallowest (BFS-first) states as fit, a whole number of 16-byte units
