@@ -303,7 +303,13 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, S
 // No CTA-wide barrier in the steady state; the only global atomics are per-warp stage flushes.
 constexpr int FK_THREADS = 1024;                 // 32 warps, one CTA per SM (shared memory bound)
 constexpr int FK_WARPS = FK_THREADS / 32;
-constexpr int FK_PAIRS = 4;                      // pairs of 512-byte warp iterations per warp chunk
+#ifndef FK_NPAIRS
+#define FK_NPAIRS 4
+#endif
+#ifndef FK_DRAIN_AT
+#define FK_DRAIN_AT 32
+#endif
+constexpr int FK_PAIRS = FK_NPAIRS;              // pairs of 512-byte warp iterations per warp chunk
 constexpr int FK_CHUNK = FK_PAIRS * 1024;        // bytes per warp chunk
 constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
 constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
@@ -615,7 +621,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
           else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), pair_rel + o, g, local_count);   // queue full: verify in place
         }
       }
-      fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, 32);       // only when a full round of survivors waits
+      fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
       cA = nA; cB = nB; tail_cur = tail_next;
     }
   }
