@@ -137,18 +137,25 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
     cudaEventRecord(g_ev0, st);
   }
   if (a->kernel_kind == 2 && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
-    // runLower on the filter kernel: scan a lowered copy of the text (same byte offsets).  If the text holds a
-    // code point whose lowering changes its UTF-8 length, fall back to the exact per-code-point walk.
+    // runLower on the filter kernel: scan a lowered copy of the text (same byte offsets).  Code points whose
+    // lowering changes their UTF-8 length stay as they are in the copy and are matched by the needle variants
+    // the automaton holds for them (am_build.cpp step 1).  Only an automaton that could not take the variants
+    // (ic_copy_exact == false) marks them instead and falls back to the exact per-code-point walk.
     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(t.dev_text) & 15);
     int rc = ws->need_aux(t.text_len + 64, 0);
     if (rc) return rc;
+    const bool keep = a->host.ic_copy_exact;
     unsigned int* d_exc = reinterpret_cast<unsigned int*>(ws->d_scalars + 16);
-    e = cudaMemsetAsync(d_exc, 0, 4, st);
-    if (e == cudaSuccess) e = launch_lower(a->dev, sa.text, t.text_len, ws->aux_a + a0, d_exc, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 16, d_exc, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    unsigned int exceptions = 0;
+    e = keep ? cudaSuccess : cudaMemsetAsync(d_exc, 0, 4, st);
+    if (e == cudaSuccess) e = launch_lower(a->dev, sa.text, t.text_len, ws->aux_a + a0, d_exc, keep, st);
+    if (!keep) {
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 16, d_exc, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) exceptions = *reinterpret_cast<unsigned int*>(ws->h_scalars + 16);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "lowering pass");
-    if (*reinterpret_cast<unsigned int*>(ws->h_scalars + 16) == 0) {
+    if (exceptions == 0) {
       sa.text = ws->aux_a + a0;
       e = launch_filter(a->dev, sa, mode, st);
     } else {

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <numeric>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "am_internal.h"
 
@@ -80,21 +81,91 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   if (rc != AM_OK) { *err = "bad lower table"; return rc; }
 
   // ---- 1. trie over bytes, insertion order ----------------------------------------------------
+  // IgnoreCase (runLower) is served by the CaseSensitive kernels over a lower-cased COPY of the text, which keeps
+  // byte offsets only if every lowering keeps its UTF-8 length.  The few code points whose lowering changes
+  // length (K U+212A -> k, Å U+212B -> å, ẞ -> ß, İ -> i, Ⱥ -> ⱥ, ...) are therefore left UNCHANGED in the copy
+  // and each needle is also inserted in the variants where such a pre-image stands for its lowered code point
+  // (same needle id).  A needle with a code point that is not its own lower case can never match (the reference
+  // lowers every text code point, Automaton.hs:478-480) and is not inserted at all.
+  std::unordered_map<uint32_t, std::vector<uint32_t>> preimages;   // lowered cp -> length-changing pre-images
+  std::unordered_set<uint32_t> image;
+  A->ic_copy_exact = true;
+  if (cs == AM_IGNORE_CASE && lower)
+    for (size_t i = 0; i < lower->n; i++) {
+      const uint32_t from = lower->pairs[i].from_cp, to = lower->pairs[i].to_cp;
+      if (from >= 128 && utf8_len(from) != utf8_len(to)) preimages[to].push_back(from);
+      image.insert(to);
+    }
+  // A code point can occur in the lowered stream iff it is its own lower case or the image of another one.
+  auto reachable = [&](uint32_t c) { return A->lower.lower(c) == c || image.count(c) != 0; };
+  // GHC's toLower is idempotent, so a length-changing code point is never itself an image; a caller-supplied
+  // table that breaks this cannot use the copy scheme (the kept original would also stand for itself).
+  for (auto& kv : preimages)
+    for (uint32_t from : kv.second)
+      if (reachable(from)) A->ic_copy_exact = false;
+  if (!A->ic_copy_exact) preimages.clear();
+  auto decode = [](const uint8_t* d, uint32_t len, uint32_t i, uint32_t* cp) -> uint32_t {   // decodeN, Utf8.hs:344-350
+    uint32_t c0 = d[i];
+    if (c0 < 0xC0) { *cp = c0; return 1; }
+    uint32_t c1 = i + 1 < len ? d[i + 1] : 0;
+    if (c0 < 0xE0) { *cp = ((c0 & 0x1F) << 6) | (c1 & 0x3F); return 2; }
+    uint32_t c2 = i + 2 < len ? d[i + 2] : 0;
+    if (c0 < 0xF0) { *cp = ((c0 & 0xF) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F); return 3; }
+    uint32_t c3 = i + 3 < len ? d[i + 3] : 0;
+    *cp = ((c0 & 7) << 18) | ((c1 & 0x3F) << 12) | ((c2 & 0x3F) << 6) | (c3 & 0x3F); return 4;
+  };
+  auto encode = [](uint32_t c, std::vector<uint8_t>* o) {
+    if (c < 0x80) o->push_back((uint8_t)c);
+    else if (c < 0x800) { o->push_back(0xC0 | (c >> 6)); o->push_back(0x80 | (c & 0x3F)); }
+    else if (c < 0x10000) { o->push_back(0xE0 | (c >> 12)); o->push_back(0x80 | ((c >> 6) & 0x3F)); o->push_back(0x80 | (c & 0x3F)); }
+    else { o->push_back(0xF0 | (c >> 18)); o->push_back(0x80 | ((c >> 12) & 0x3F)); o->push_back(0x80 | ((c >> 6) & 0x3F)); o->push_back(0x80 | (c & 0x3F)); }
+  };
   Builder B;
   B.edge.reserve(n * 8 + 16);
-  std::vector<uint32_t> term(n);
+  std::vector<std::pair<uint32_t, uint32_t>> terms;   // (trie state, needle index); a needle may end in several states (variants)
+  terms.reserve(n);
   std::vector<uint32_t> len_bytes(n), len_cps(n);
   A->min_len = 0xFFFFFFFFu; A->max_len = 0; A->max_len_cps = 0; A->num_empty = 0;
+  constexpr uint64_t MAX_VARIANTS = 64;
+  auto insert = [&](const uint8_t* d, uint32_t len, uint32_t id) {
+    uint32_t s = 0;
+    for (uint32_t k = 0; k < len; k++) s = B.add(s, d[k]);
+    terms.emplace_back(s, id);
+    if (len > 0) { A->min_len = std::min(A->min_len, len); A->max_len = std::max(A->max_len, len); }
+  };
   for (size_t i = 0; i < n; i++) {
     if (needles[i].len < 0 || needles[i].off < 0 || (needles[i].len > 0 && !needles[i].ptr)) { *err = "bad needle slice"; return AM_E_BADARG; }
     if ((uint64_t)needles[i].len >= (1ull << 24)) { *err = "needle longer than 16 MiB"; return AM_E_BADARG; }
     const uint8_t* d = needles[i].ptr + needles[i].off;
-    uint32_t len = (uint32_t)needles[i].len, s = 0, cps = 0;
-    for (uint32_t k = 0; k < len; k++) { s = B.add(s, d[k]); cps += (d[k] & 0xC0) != 0x80; }
-    term[i] = s; len_bytes[i] = len; len_cps[i] = cps;
-    if (len == 0) { A->num_empty++; continue; }
-    A->min_len = std::min(A->min_len, len); A->max_len = std::max(A->max_len, len);
+    const uint32_t len = (uint32_t)needles[i].len;
+    uint32_t cps = 0;
+    for (uint32_t k = 0; k < len; k++) cps += (d[k] & 0xC0) != 0x80;
+    len_bytes[i] = len; len_cps[i] = cps;
+    if (len == 0) A->num_empty++;
     A->max_len_cps = std::max(A->max_len_cps, cps);
+    if (cs != AM_IGNORE_CASE) { insert(d, len, (uint32_t)i); continue; }
+    // IgnoreCase: dead needles, variants
+    std::vector<uint32_t> ncp;
+    bool dead = false;
+    for (uint32_t k = 0; k < len;) { uint32_t c; k += decode(d, len, k, &c); ncp.push_back(c); if (!reachable(c)) dead = true; }
+    if (dead) continue;                                   // can never match: every text code point is lowered first
+    insert(d, len, (uint32_t)i);
+    uint64_t combos = 1;
+    for (uint32_t c : ncp) { auto it = preimages.find(c); if (it != preimages.end()) combos *= 1 + it->second.size(); if (combos > MAX_VARIANTS) break; }
+    if (combos == 1) continue;
+    if (combos > MAX_VARIANTS) { A->ic_copy_exact = false; continue; }   // too many variants: this automaton uses the sentinel + fallback scheme
+    std::vector<uint32_t> choice(ncp.size(), 0);
+    for (uint64_t v = 1; v < combos; v++) {                // odometer over the pre-image choices (0 = the lowered code point itself)
+      for (size_t p = 0; p < ncp.size(); p++) {
+        auto it = preimages.find(ncp[p]);
+        const uint32_t radix = it == preimages.end() ? 1 : 1 + (uint32_t)it->second.size();
+        if (++choice[p] < radix) break;
+        choice[p] = 0;
+      }
+      std::vector<uint8_t> bytes;
+      for (size_t p = 0; p < ncp.size(); p++) encode(choice[p] == 0 ? ncp[p] : preimages[ncp[p]][choice[p] - 1], &bytes);
+      insert(bytes.data(), (uint32_t)bytes.size(), (uint32_t)i);
+    }
   }
   if (A->min_len == 0xFFFFFFFFu) A->min_len = 0;
   const uint32_t S = (uint32_t)B.parent.size();
@@ -186,15 +257,17 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   A->rank_bits = 1; while ((1ull << A->rank_bits) < n) A->rank_bits++;
 
   A->own_off.assign(S + 1, 0);
-  for (size_t i = 0; i < n; i++) A->own_off[new_id[term[i]] + 1]++;
+  for (auto& tm : terms) A->own_off[new_id[tm.first] + 1]++;
   for (uint32_t s = 0; s < S; s++) A->own_off[s + 1] += A->own_off[s];
-  A->own_rank.resize(n);
   {
     std::vector<uint32_t> fill(A->own_off.begin(), A->own_off.end() - 1);
-    for (uint32_t r = 0; r < n; r++) {  // ascending rank => within a state: index descending (later duplicate first)
-      uint32_t s = new_id[term[A->id_of_rank[r]]];
-      A->own_rank[fill[s]++] = r;
-    }
+    // ascending rank within a state => index descending (later duplicate first)
+    std::vector<std::pair<uint32_t, uint32_t>> by_rank;   // (rank, state)
+    by_rank.reserve(terms.size());
+    for (auto& tm : terms) by_rank.emplace_back(A->rank_of_id[tm.second], new_id[tm.first]);
+    std::sort(by_rank.begin(), by_rank.end());
+    A->own_rank.resize(terms.size());
+    for (auto& rs : by_rank) A->own_rank[fill[rs.second]++] = rs.first;
   }
   // chain(s) = own(s) ++ chain(fail s), but only code-point-boundary states report, and the root
   // itself never reports (its own list -- the empty needles -- is only inherited).

@@ -71,6 +71,7 @@ struct HostAutomaton {
   uint32_t min_len = 0, max_len = 0;   // bytes, over non-empty needles
   uint32_t max_len_cps = 0;
   uint32_t num_empty = 0;              // empty needles (reported after every successful transition, A.4)
+  bool ic_copy_exact = true;           // IgnoreCase: needle variants cover every length-changing pre-image (no fallback needed)
   uint32_t q = 0;                      // filter q-gram length, 0 => filter kernel not applicable
   uint32_t rank_bits = 1;
   uint64_t halo_bytes = 0;             // bytes a shard needs before its report range

@@ -649,10 +649,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
 // ẞ U+1E9E, İ U+0130, Ⱥ, Ⱦ, ...) -- the lowered text has the same byte offsets as the original, so the scan
 // can run the CaseSensitive kernels on a lowered COPY of the text.  This kernel writes that copy: one thread
 // per 16-byte granule, SWAR for all-ASCII granules, decode -> table -> re-encode otherwise.  A code point
-// whose lowering changes length is overwritten with 0xFF bytes (never part of a valid UTF-8 needle) and
-// counted; the host then falls back to the exact per-code-point walk kernel for that text.
+// whose lowering changes length is handled in one of two ways:
+//  * keep = 1 (the automaton holds the needle variants for every such code point, am_build.cpp step 1):
+//    it is left unchanged in the copy, where the variant needles match it -- exact, no second pass;
+//  * keep = 0: it is overwritten with 0xFF bytes (never part of a valid UTF-8 needle) and counted; the host
+//    then falls back to the exact per-code-point walk kernel for that text.
 __global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_t* text, uint64_t text_len, uint8_t* out /* same misalignment as text */,
-                                                    unsigned int* exceptions) {
+                                                    unsigned int* exceptions, int keep) {
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(text);
   const uint32_t a0 = (uint32_t)(addr0 & 15);
   const uint4* in16 = reinterpret_cast<const uint4*>(addr0 - a0);
@@ -705,6 +708,7 @@ __global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_
       else if (l < 0x10000u) { enc[0] = 0xE0u | (l >> 12); enc[1] = 0x80u | ((l >> 6) & 0x3Fu); enc[2] = 0x80u | (l & 0x3Fu); elen = 3; }
       else { enc[0] = 0xF0u | (l >> 18); enc[1] = 0x80u | ((l >> 12) & 0x3Fu); enc[2] = 0x80u | ((l >> 6) & 0x3Fu); enc[3] = 0x80u | (l & 0x3Fu); elen = 4; }
       const bool same = elen == len;
+      if (!same && keep) continue;                                // res already holds the original bytes
       if (!same && p >= 4 && p < 20) atomicAdd(exceptions, 1u);   // counted once, by the granule that holds the lead byte
       for (uint32_t k = 0; k < len; k++) {
         const int qi = p + (int)k - 4;
@@ -829,12 +833,12 @@ cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cu
   return launch_filter_m<MODE_EMIT>(A, a, st);
 }
 
-cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, cudaStream_t st) {
+cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, bool keep, cudaStream_t st) {
   if (text_len == 0) return cudaSuccess;
   const uint64_t nvec = ((reinterpret_cast<uintptr_t>(text) & 15) + text_len + 15) >> 4;
   const unsigned blocks = (unsigned)std::min<uint64_t>((nvec + 255) / 256, (uint64_t)sm_count() * 16);
   g_kernel_launches++;
-  lower_kernel<<<blocks, 256, 0, st>>>(A, text, text_len, out, exceptions);
+  lower_kernel<<<blocks, 256, 0, st>>>(A, text, text_len, out, exceptions, keep ? 1 : 0);
   return cudaGetLastError();
 }
 

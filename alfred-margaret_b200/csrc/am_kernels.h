@@ -17,7 +17,7 @@ cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cuda
 cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);
 
 // IgnoreCase front end of the filter kernel: lowered copy of the text (+ count of length-changing code points).
-cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, cudaStream_t st);
+cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, bool keep, cudaStream_t st);
 size_t sort_temp_bytes(uint64_t n, int end_bit);
 cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_t* out, uint64_t n, int end_bit, cudaStream_t st);
 cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st);

@@ -55,7 +55,11 @@ def test_host_image_introspection(oracle):
     needles = ["groß", "öffnung", "tür", ""]
     mi = automaton.AcMachine([(n, ()) for n in needles], case_sensitivity=1, device=-2)
     assert mi.info()["kernel_kind"] == 1                      # IgnoreCase / empty needle -> general walk kernel
-    assert mi.info()["num_states"] == 1 + sum(len(n.encode()) for n in needles)
+    # + the IgnoreCase variant "groẞ" (ẞ U+1E9E lowers to ß with another UTF-8 length): 3 more bytes after "gro"
+    assert mi.info()["num_states"] == 1 + sum(len(n.encode()) for n in needles) + len("ẞ".encode())
+    # needles that are not lower case can never match runLower and are not inserted
+    md = automaton.AcMachine([("ABC", 0), ("\u212a", 1), ("ab", 2)], case_sensitivity=1, device=-2)
+    assert md.info()["num_states"] == 3
     assert oracle.Machine(needles).num_states == 1 + sum(len(n) for n in needles)
 
 

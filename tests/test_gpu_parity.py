@@ -272,6 +272,41 @@ def test_ignore_case_length_preserving_text(am, oracle, lower_dense):
         assert m.count_matches(hay) == len(want)
 
 
+def test_ignore_case_length_changing_variants(am, oracle, lower_dense):
+    """Code points whose lower case has another UTF-8 length (K U+212A -> k, Å U+212B -> å, ẞ -> ß, İ -> i,
+    Ⱥ -> ⱥ, Ⱦ -> ⱦ): the filter path keeps them in the lowered copy and matches them through needle variants
+    (am_build.cpp step 1); needles that are not lower case can never match (Automaton.hs:478-480); a needle
+    with too many variants switches the automaton to the mark-and-fall-back scheme.  All must equal runLower."""
+    rng = np.random.default_rng(91)
+    cps = list("kKaAiIsSbt ") * 2 + list("\u212a\u212båÅßẞ\u0130ⱥȺⱦȾ") * 2 + list("é𝄞")
+    hay = "".join(rng.choice(cps, size=200000)).encode("utf-8")
+    pool = list("kaist") + list("åßⱥⱦé")
+    base = sorted({"".join(rng.choice(pool, size=int(rng.integers(1, 6)))) for _ in range(300)})
+    sets = {
+        "variants": base,
+        "dead needles": base[:50] + ["K", "\u212a", "ak\u212b", "Åk", "ẞ", "İi", "kȺ"],    # never match
+        "fallback": base[:50] + ["kkkkkkk", "iiißßßkk"],                                  # > 64 variants each
+        "empty needle": base[:20] + [""],
+    }
+    for name, needles in sets.items():
+        ln = [n.encode("utf-8") for n in needles]
+        want = oracle.Machine(ln).find_all(hay, cs=1, lower=lower_dense, cap=1 << 22)
+        assert len(want) > 1000
+        for kind in (0, 1, 2):
+            if kind == 2 and "" in needles:
+                continue
+            m = machine(am, ln, cs=1, force_kernel=kind)
+            for off in (0, 5):
+                buf = np.frombuffer(b"\xe2" * off + hay, dtype=np.uint8)
+                got = m.find_all(am.utf8.Text(buf, off, len(hay)))
+                assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (name, kind, off)
+            assert m.count_matches(hay) == len(want), (name, kind)
+    # a dead needle alone: no match at all, on either kernel
+    for kind in (0, 1):
+        m = machine(am, ["\u212a".encode(), b"K"], cs=1, force_kernel=kind)
+        assert m.count_matches(hay) == 0 and not m.contains_any(hay)
+
+
 def test_config3_downscaled_ignore_case(am, oracle, lower_dense):
     """BASELINE.json config 3 down-scaled: 2 000 lower-case needles (20 % with non-ASCII code points), IgnoreCase,
     an 8 MiB mixed-case UTF-8 haystack with 1/2/3/4-byte code points incl. length-changing ones (K, Å, ẞ, İ, Ⱥ)."""
