@@ -1,0 +1,534 @@
+// am_filter.cu -- the q-gram filter scan kernel of libam_b200 (see am_kernels.cu for the file-level notes).
+#include <cstddef>
+
+#include "am_device.cuh"
+#include "am_kernels.h"
+
+namespace am {
+
+// =====================================================================================================
+// filter_kernel
+// =====================================================================================================
+// Per warp, per 4 KiB chunk, in pairs of 512-byte iterations:
+//   1. stream two 16-byte granules per lane from HBM (next pair prefetched into registers) and mirror
+//      them into the warp's 1 KiB shared-memory window;
+//   2. probe the bank-private q-gram bitmap once per text position (32 candidate bits per lane);
+//   3. pop the candidate bits: re-read the exact q-gram from the window, test it against the exact
+//      second-level table T2 (shared memory) -> "survivors" (true q-gram prefix hits, ~0.2 %);
+//   4. survivors are queued per warp and, 32 at a time, walked through the goto trie in HBM/L2
+//      (dense: all lanes busy); matches go to a per-warp stage, flushed with one global atomic.
+// No CTA-wide barrier in the steady state; the only global atomics are per-warp stage flushes.
+constexpr int FK_THREADS = 1024;                 // 32 warps, one CTA per SM (shared memory bound)
+constexpr int FK_WARPS = FK_THREADS / 32;
+#ifndef FK_NPAIRS
+#define FK_NPAIRS 4
+#endif
+#ifndef FK_DRAIN_AT
+#define FK_DRAIN_AT 32
+#endif
+constexpr int FK_PAIRS = FK_NPAIRS;              // pairs of 512-byte warp iterations per warp chunk
+constexpr int FK_CHUNK = FK_PAIRS * 1024;        // bytes per warp chunk
+constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
+constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
+constexpr int FK_SQ = 64;                        // survivor queue entries per warp
+constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
+constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
+// Build-time variants (A/B-tested on the GPU):
+//   (a warp-scan "dense" compaction of the candidates was A/B-tested and was not faster; removed)
+//   FK_PF         distance (in CTA tiles) of the bulk L2 prefetch issued ahead of the streaming loads; the
+//                 register double-buffer alone keeps too few bytes in flight to cover HBM latency
+#ifndef FK_PF
+#define FK_PF 0
+#endif
+//   FK_DEBUG      compile the stage-isolation switches (AM_DEBUG_FLAGS=1: probes only, 2: no survivor walk)
+#ifndef FK_DEBUG
+#define FK_DEBUG 0
+#endif
+//   FK_LOOP2      second form of the main loop (pair loop unrolled by two, clamped instead of guarded loads)
+#ifndef FK_LOOP2
+#define FK_LOOP2 1
+#endif
+
+struct FilterSmem {
+  uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
+  uint32_t t2[T2_WORDS];                         // 32 KiB
+  uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
+  uint2 sq[FK_WARPS][FK_SQ];                     // 16 KiB: (offset from v_begin, q-gram)
+  unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
+  uint32_t sq_n[FK_WARPS];
+  uint32_t wkeys_n[FK_WARPS];
+  unsigned long long red[FK_WARPS];
+  alignas(8) unsigned long long mbar;
+};
+
+// Context of the rare out-of-line work (survivor walk, flushes); everything in it is recomputed from kernel
+// parameters and the thread index where it is used, so it costs the hot loop no registers.
+struct FilterCtx {
+  uint64_t v_begin; uint32_t a0, warp, lane;
+  __device__ __forceinline__ FilterCtx(const ScanArgs& a, uint64_t vb)
+      : v_begin(vb), a0((uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15)), warp(threadIdx.x >> 5), lane(threadIdx.x & 31) {}
+};
+
+template <int MODE>
+__device__ __forceinline__ void fk_emit(const ScanArgs& a, FilterSmem* sm, uint32_t warp, unsigned long long key) {
+  const uint32_t i = atomicAdd(&sm->wkeys_n[warp], 1u);
+  if (i < FK_WSTAGE) { sm->wkeys[warp][i] = key; return; }
+  const unsigned long long g = atomicAdd(a.d_count, 1ull);  // stage full: direct append
+  if (g < a.cap) a.d_keys[g] = key;
+}
+
+// Flush the warp's staged keys (call with the warp converged).
+__device__ __forceinline__ void fk_flush(const ScanArgs& a, FilterSmem* sm, uint32_t warp, uint32_t lane, uint32_t min_fill) {
+  __syncwarp();
+  uint32_t n = sm->wkeys_n[warp];
+  if (n > FK_WSTAGE) n = FK_WSTAGE;
+  if (n < min_fill || n == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(a.d_count, (unsigned long long)n);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (lane < n && base + lane < a.cap) a.d_keys[base + lane] = sm->wkeys[warp][lane];
+  __syncwarp();
+  if (lane == 0) sm->wkeys_n[warp] = 0;
+  __syncwarp();
+}
+
+// Walk the goto trie from a survivor (its q-gram is a prefix of some needle, or a rare T2 alias):
+// report every needle that is a prefix of text[i..].  No failure links are needed because every
+// start position is tried (failure-less, position-parallel formulation of Aho-Corasick).
+template <int MODE>
+__device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                               uint32_t v_rel, uint32_t g, unsigned long long& local_count) {
+  const uint64_t v = c.v_begin + v_rel;
+  if (v < c.a0) return;
+  const uint64_t i = v - c.a0;
+  if (i + A.min_len > a.text_len) return;
+  uint32_t idx = jump_hash(g) & A.jump_mask;
+  uint32_t st;
+  for (;;) {
+    const uint2 s = __ldg(reinterpret_cast<const uint2*>(A.jump) + idx);
+    if (s.y == NONE) return;
+    if (s.x == g) { st = s.y; break; }
+    idx = (idx + 1) & A.jump_mask;
+  }
+  uint32_t d = A.q;
+  for (;;) {
+    if (st & OWN_FLAG) {
+      const uint64_t end = i + d;
+      if (end > a.report_begin) {
+        const uint32_t s = st & ID_MASK;
+        const uint32_t olo = __ldg(A.own_off + s), ohi = __ldg(A.own_off + s + 1);
+        if (MODE == MODE_COUNT) local_count += ohi - olo;
+        else if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
+        else
+          for (uint32_t j = olo; j < ohi; j++)
+            fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+      }
+    }
+    if (i + d >= a.text_len) return;
+    const uint32_t ch = __ldg(a.text + i + d);
+    st = edge_lookup(A, st & ID_MASK, ch);
+    if (st == NONE) return;
+    d++;
+  }
+}
+
+// Drain the warp's survivor queue (warp converged on entry and exit).
+template <int MODE>
+__device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                           unsigned long long& local_count, uint32_t n) {
+  for (uint32_t k = c.lane; k < n; k += 32) {
+    const uint2 e = sm->sq[c.warp][k];
+    fk_deep_verify<MODE>(A, a, sm, c, e.x, e.y, local_count);
+  }
+  __syncwarp();
+  if (c.lane == 0) sm->sq_n[c.warp] = 0;
+  __syncwarp();
+  if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
+}
+
+template <int MODE>
+__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+                                         unsigned long long& local_count, uint32_t min_fill) {
+  __syncwarp();
+  uint32_t n = sm->sq_n[c.warp];
+  if (n > FK_SQ) n = FK_SQ;
+  if (n < min_fill || n == 0) return;
+  fk_drain_body<MODE>(A, a, sm, c, local_count, n);
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)); return v;
+}
+
+// 16 probes of one granule: w[0..3] own words, w[4] the word that follows.  `filt_lane` is the shared
+// address of this lane's private copy of the bitmap.
+template <bool Q4>
+__device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmask, uint32_t krow, uint32_t m,
+                                               uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+  const uint32_t w[5] = {w0, w1, w2, w3, w4};
+  // positions are visited last-to-first so that, after both granules, bit P of the mask is position P
+#pragma unroll
+  for (int k = 3; k >= 0; k--) {
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+      uint32_t g = j == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * j);
+      if (!Q4) g &= qmask;
+#if FK_WB
+      const uint32_t y = g * HASH_MUL;                     // bit index = low 5 bits, row = top bits
+      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);   // SHF + IMAD(UR) + LDS
+#else
+      const uint32_t y = (g * HASH_MUL) >> 15;             // bits 0..4 bit index, top FILTER_ROWBITS bits row
+      const uint32_t word = lds32((y & (((1u << FILTER_ROWBITS) - 1u) << (17 - FILTER_ROWBITS))) + filt_lane);
+#endif
+      const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
+      m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
+    }
+  }
+  return m;
+}
+
+// Stride-2 form of the 16 probes (q = 4, FK_S2): for every even position p ONE bitmap word answers both "a needle
+// starts at p" and "a needle starts at p + 1".  The row is hashed from text[p+1..p+4) -- the 4-gram at p + 1 times
+// HASH_MUL << 8, which discards its top byte -- and the two bits are picked by rotating the word by text[p] and by
+// text[p + 4] (SHF uses the low 5 bits of the register, so any register whose low byte is that text byte serves).
+// Per two text bytes: 1.5 + 1 + 2 + 2 ALU-pipe instructions, 2 IMAD, 1 LDS (stride-1: 7.5, 4, 2).
+__device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t m,
+                                                  uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+  const uint32_t w[5] = {w0, w1, w2, w3, w4};
+  // h[k]: register whose low byte is text[4k + 2]
+  uint32_t h[5];
+#pragma unroll
+  for (int k = 0; k < 4; k++) h[k] = __funnelshift_r(w[k], w[k + 1], 16);
+  h[4] = w[4] >> 16;
+#pragma unroll
+  for (int k = 3; k >= 0; k--) {
+    {  // p = 4k + 2: positions 4k + 3 (cell B, private byte text[4k + 6]) and 4k + 2 (cell A, text[4k + 2])
+      const uint32_t y = __funnelshift_r(w[k], w[k + 1], 24) * HASH_MUL_S2;
+      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);
+      m = __funnelshift_l(__funnelshift_l(word, word, h[k + 1]), m, 1);
+      m = __funnelshift_l(__funnelshift_l(word, word, h[k]), m, 1);
+    }
+    {  // p = 4k: positions 4k + 1 (cell B, text[4k + 4]) and 4k (cell A, text[4k])
+      const uint32_t y = __funnelshift_r(w[k], w[k + 1], 8) * HASH_MUL_S2;
+      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);
+      m = __funnelshift_l(__funnelshift_l(word, word, w[k + 1]), m, 1);
+      m = __funnelshift_l(__funnelshift_l(word, word, w[k]), m, 1);
+    }
+  }
+  return m;
+}
+
+// Second-level test of one candidate at byte offset `o` of the warp's window: recover the exact q-gram,
+// look it up in T2 (exact keys + the byte that must follow, or a bitmap for large needle sets).
+// win_s / t2_s: shared-space addresses of the warp's window and of T2.
+template <bool Q4, bool T2X>
+__device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s, uint32_t t2_s, uint32_t o, uint32_t* g_out) {
+  const uint32_t wa = win_s + (o & ~3u);
+  const uint32_t lo = lds32(wa), hi = lds32(wa + 4);
+  const uint32_t sh = (o & 3u) * 8u;
+  uint32_t g = __funnelshift_r(lo, hi, sh);
+  if (!Q4) g &= A.qmask;
+  *g_out = g;
+  if (T2X) {
+    uint32_t hb = (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS);
+    uint32_t aux;
+    for (;;) {
+      const uint4 b = lds128(t2_s + (hb << 4));
+      if (b.x == g) { aux = b.y; break; }
+      if (b.z == g) { aux = b.w; break; }
+      if (!(b.w & T2_AUX_OVERFLOW)) return false;          // the common exit: one probe
+      hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
+    }
+    if (aux & T2_AUX_ANY) return true;
+    uint32_t nb;                                           // text byte right after the q-gram
+    if (Q4) nb = (hi >> sh) & 0xFFu;
+    else nb = (uint32_t)((((unsigned long long)hi << 32) | lo) >> (sh + 8u * A.q)) & 0xFFu;
+    return nb == (aux & 0xFFu);
+  } else {
+    const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
+    return (lds32(t2_s + ((b2 >> 5) << 2)) >> (b2 & 31)) & 1u;
+  }
+}
+
+template <int MODE, bool Q4, bool T2X>
+__global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FilterSmem* sm = reinterpret_cast<FilterSmem*>(smem_raw);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- stage the filter bitmap and T2 into shared memory with TMA bulk copies -----------------------
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm->mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t total = FILTER_WORDS * 4 + T2_WORDS * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm->mbar)), "r"(total) : "memory");
+    constexpr uint32_t CH = 16384;
+    for (uint32_t off = 0; off < FILTER_WORDS * 4; off += CH)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->filter) + off)),
+                   "l"(reinterpret_cast<const unsigned char*>(A.filter) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
+                   : "memory");
+    for (uint32_t off = 0; off < T2_WORDS * 4; off += CH)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(reinterpret_cast<unsigned char*>(sm->t2) + off)),
+                   "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
+                   : "memory");
+  }
+  if (lane == 0) { sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0; }
+  __syncthreads();
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&sm->mbar)), "r"(0u) : "memory");
+  }
+
+#if FK_LOOP2
+  // ---- main loop, second form ------------------------------------------------------------------------------------
+  // Same pipeline (everything a pair needs was requested one pair earlier), restated so that the hot path carries
+  // no bookkeeping: the pair loop is unrolled by two (register ping-pong instead of moves), the position of the next
+  // pair is one warp-uniform granule index, loads that could leave the text are CLAMPED to its last granule instead
+  // of being guarded (bytes beyond the text only ever reach candidates that the exact verification rejects on
+  // bounds), shared-memory addresses are compile-time offsets from the CTA's dynamic shared memory base.
+  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text (>= 1 here)
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & (FK_COPIES - 1u)) << 2);
+  const uint32_t win_s = smem0 + (uint32_t)offsetof(FilterSmem, window) + warp * (FK_WIN_WORDS * 4u);
+  const uint32_t win_lane = win_s + (lane << 4);
+  const uint32_t t2_s = smem0 + (uint32_t)offsetof(FilterSmem, t2);
+  unsigned long long local_count = 0;
+
+  auto load_pair = [&](uint64_t g, uint4& qa, uint4& qb, uint32_t& tail) {   // g: first granule of the pair (warp-uniform)
+    if (g + 65 <= nvec) {                                  // granules g .. g + 64 exist
+      const uint4* p = base16 + g + lane;
+      qa = ld_stream_v4(p);
+      qb = ld_stream_v4(p + 32);
+      tail = __ldg(reinterpret_cast<const uint32_t*>(base16 + g + 64));
+    } else {
+      const uint64_t last = nvec - 1;
+      const uint64_t ga = g + lane < last ? g + lane : last, gb = g + lane + 32 < last ? g + lane + 32 : last;
+      const uint64_t gt = g + 64 < last ? g + 64 : last;
+      qa = ld_stream_v4(base16 + ga);
+      qb = ld_stream_v4(base16 + gb);
+      tail = __ldg(reinterpret_cast<const uint32_t*>(base16 + gt));
+    }
+  };
+  auto process_pair = [&](const uint4& qa, const uint4& qb, uint32_t tail, uint32_t pair_rel) {
+    // mirror the pair into the window (exact q-gram recovery for the few candidates)
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane), "r"(qa.x), "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane + 512u), "r"(qb.x), "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s + 1024u), "r"(tail) : "memory");
+    const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? qb.x : qa.x, (lane + 1) & 31);
+    const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail : qb.x, (lane + 1) & 31);
+    uint32_t m = 0;                                        // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
+    if (Q4 && FK_S2) {
+      m = fk_probe16_s2(filt_lane, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
+      m = fk_probe16_s2(filt_lane, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
+    } else {
+      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
+      m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
+    }
+    __syncwarp();
+#if FK_DEBUG
+    if (a.debug & 1u) { local_count += __popc(m); m = 0; }
+#endif
+    // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
+    while (m) {
+      uint32_t P;
+      asm("bfind.u32 %0, %1;" : "=r"(P) : "r"(m));         // highest candidate position
+      m ^= 1u << P;
+      const uint32_t o = (P & 16u) * 31u + P;              // byte offset from the lane's granule A: (P >> 4) * 512 + (P & 15)
+      uint32_t g;
+      if (fk_phase_a<Q4, T2X>(A, win_lane, t2_s, o, &g)) {
+#if FK_DEBUG
+        if (a.debug & 2u) { local_count++; continue; }
+#endif
+        const uint32_t rel = pair_rel + o + (lane << 4);
+        const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
+        if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(rel, g);
+        else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
+      }
+    }
+    fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
+  };
+
+  static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
+  const uint64_t tile_stride_granules = (uint64_t)gridDim.x * (FK_TILE / 16);
+  uint64_t g_next = ((v_begin + (uint64_t)blockIdx.x * FK_TILE + (uint64_t)warp * FK_CHUNK) >> 4);   // granule of the pair in flight
+  uint4 cA, cB, nA, nB;
+  uint32_t tC, tN;
+  if (blockIdx.x < num_tiles) load_pair(g_next, cA, cB, tC);
+  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
+    const uint32_t chunk_rel = (uint32_t)(tile * FK_TILE) + warp * FK_CHUNK;   // this warp's chunk, relative to v_begin
+#pragma unroll 1
+    for (int pair = 0; pair < FK_PAIRS; pair += 2) {
+      g_next += 64;                                        // odd pair of the same chunk
+      load_pair(g_next, nA, nB, tN);
+      process_pair(cA, cB, tC, chunk_rel + (uint32_t)pair * 1024u);
+      g_next += pair + 2 < FK_PAIRS ? 64 : tile_stride_granules - (FK_PAIRS - 1) * 64;   // next even pair: same chunk, or this warp's chunk in the CTA's next tile
+      load_pair(g_next, cA, cB, tC);                       // beyond the CTA's last tile this is a clamped, unused load
+      process_pair(nA, nB, tN, chunk_rel + (uint32_t)pair * 1024u + 1024u);
+    }
+  }
+#else
+
+  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
+  const uint32_t a0 = (uint32_t)(addr0 & 15);
+  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
+  const uint32_t* base32 = reinterpret_cast<const uint32_t*>(base16);
+  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text
+  const uint32_t filt_lane = smem_u32(sm->filter) + ((lane & (FK_COPIES - 1u)) << 2);   // this lane's private copy (bank)
+  uint32_t* win = sm->window[warp];
+  const uint32_t win_s = smem_u32(win), t2_s = smem_u32(sm->t2);
+  unsigned long long local_count = 0;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+  // Software pipeline over (tile, pair): everything a pair needs was requested one pair earlier -- its two
+  // granules per lane and the word that follows the pair -- including across chunk and tile boundaries.
+  // Interior tiles (everything they and their successor's first pair touch lies inside the text) use
+  // unguarded loads at immediate offsets from one per-lane pointer; edge tiles take the guarded path.
+  auto pair_granule = [&](uint64_t tile, int pair) -> uint64_t {   // first 16-byte granule of (tile, pair) for this warp
+    return ((v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK) >> 4) + (uint64_t)pair * 64;
+  };
+  auto load_pair_guarded = [&](uint64_t g, uint4& A, uint4& B, uint32_t& tail) {
+    A = zero4; B = zero4; tail = 0;
+    if (g + lane < nvec) A = ld_stream_v4(base16 + g + lane);
+    if (g + 32 + lane < nvec) B = ld_stream_v4(base16 + g + 32 + lane);
+    if (lane == 0 && g + 64 < nvec) tail = __ldg(base32 + (g + 64) * 4);
+  };
+  uint4 cA = zero4, cB = zero4;
+  uint32_t tail_cur = 0;
+  if (blockIdx.x < num_tiles) load_pair_guarded(pair_granule(blockIdx.x, 0), cA, cB, tail_cur);
+  const uint64_t tile_stride_granules = (uint64_t)gridDim.x * (FK_TILE / 16);
+  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
+    const uint64_t chunk_v0 = v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK;  // granule-aligned virtual index
+    const uint32_t chunk_rel = (uint32_t)(chunk_v0 - v_begin);
+    const uint64_t g0 = chunk_v0 >> 4;
+    const bool has_next = tile + gridDim.x < num_tiles;
+    // last granule touched from this tile: the tail word of the NEXT tile's first pair (or of our last pair)
+    const bool interior = (has_next ? g0 + tile_stride_granules + 64 + 1 : g0 + FK_PAIRS * 64 + 1) < nvec;
+    const uint4* pl = base16 + g0 + lane;
+#if FK_PF > 0
+    if (lane == 0) {   // pull this warp's chunk of a later tile into L2 (one TMA-style bulk prefetch, no registers)
+      const uint64_t pv = g0 + (uint64_t)FK_PF * tile_stride_granules;
+      if (tile + (uint64_t)FK_PF * gridDim.x < num_tiles && pv + FK_CHUNK / 16 <= nvec)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base16 + pv), "r"((uint32_t)FK_CHUNK) : "memory");
+    }
+#endif
+#pragma unroll 1
+    for (int pair = 0; pair < FK_PAIRS; pair++) {
+      // request the next pair (same chunk, or the first pair of this warp's chunk in the CTA's next tile)
+      uint4 nA = zero4, nB = zero4;
+      uint32_t tail_next = 0;
+      const bool same = pair + 1 < FK_PAIRS;
+      if (interior) {
+        if (same || has_next) {
+          const uint4* pn = same ? pl + 64 * (pair + 1) : pl + tile_stride_granules;   // this lane's granule of the NEXT pair
+          nA = ld_stream_v4(pn);
+          nB = ld_stream_v4(pn + 32);
+          if (lane == 0) tail_next = __ldg(reinterpret_cast<const uint32_t*>(pn + 64));
+        }
+      } else if (same || has_next) {
+        load_pair_guarded(pair_granule(same ? tile : tile + gridDim.x, same ? pair + 1 : 0), nA, nB, tail_next);
+      }
+      // mirror the pair into the window (exact q-gram recovery for the few candidates)
+      reinterpret_cast<uint4*>(win)[lane] = cA;
+      reinterpret_cast<uint4*>(win)[32 + lane] = cB;
+      if (lane == 0) win[256] = tail_cur;
+      const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
+      const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail_cur : cB.x, (lane + 1) & 31);
+      uint32_t m = 0;                                      // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
+      if (Q4 && FK_S2) {
+        m = fk_probe16_s2(filt_lane, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
+        m = fk_probe16_s2(filt_lane, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
+      } else {
+        m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
+        m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
+      }
+      __syncwarp();
+#if FK_DEBUG
+      if (a.debug & 1u) { local_count += __popc(m); m = 0; }
+#endif
+      const uint32_t pair_rel = chunk_rel + (uint32_t)pair * 1024u;
+      // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
+      while (m) {
+        const uint32_t P = 31u - __clz(m);                    // FLO: highest candidate position
+        m ^= 1u << P;
+        const uint32_t o = (P & 16u) * 31u + P + (lane << 4);  // byte offset inside the pair: (P >> 4) * 512 + lane * 16 + (P & 15)
+        uint32_t g;
+        if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
+#if FK_DEBUG
+          if (a.debug & 2u) { local_count++; continue; }
+#endif
+          const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
+          if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
+          else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), pair_rel + o, g, local_count);   // queue full: verify in place
+        }
+      }
+      fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
+      cA = nA; cB = nB; tail_cur = tail_next;
+    }
+  }
+#endif
+  fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, 1);
+  if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
+
+  if (MODE == MODE_COUNT) {
+    for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
+    if (lane == 0) sm->red[warp] = local_count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long s = 0;
+      for (int i = 0; i < FK_WARPS; i++) s += sm->red[i];
+      if (s) atomicAdd(a.d_count, s);
+    }
+  }
+}
+
+template <int MODE, bool Q4, bool T2X>
+static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
+  if (a.text_len <= a.report_begin) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4, T2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
+  // first start position that can produce a match ending after report_begin
+  const uint64_t first = a.report_begin + 1 > A.max_len ? a.report_begin + 1 - A.max_len : 0;
+  const uint64_t v_end = a0 + a.text_len;
+  for (uint64_t v0 = (first + a0) & ~15ull; v0 < v_end; v0 += FK_SPAN) {
+    const uint64_t span = v_end - v0 < FK_SPAN ? v_end - v0 : FK_SPAN;
+    const uint64_t tiles = (span + FK_TILE - 1) / FK_TILE;
+    const uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
+    g_kernel_launches++;
+    filter_kernel<MODE, Q4, T2X><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <int MODE>
+static cudaError_t launch_filter_m(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
+  const bool q4 = A.q == 4, x = A.t2_exact != 0;
+  if (q4) return x ? launch_filter_t<MODE, true, true>(A, a, st) : launch_filter_t<MODE, true, false>(A, a, st);
+  return x ? launch_filter_t<MODE, false, true>(A, a, st) : launch_filter_t<MODE, false, false>(A, a, st);
+}
+
+cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {
+  if (mode == MODE_COUNT) return launch_filter_m<MODE_COUNT>(A, a, st);
+  if (mode == MODE_ANY) return launch_filter_m<MODE_ANY>(A, a, st);
+  return launch_filter_m<MODE_EMIT>(A, a, st);
+}
+
+int filter_kernel_smem_bytes() { return (int)sizeof(FilterSmem); }
+
+}  // namespace am

@@ -106,19 +106,30 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
 
 inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
 // Build-time variants of the filter kernel (A/B-tested on the GPU):
-//   FK_COPIES  private copies of the q-gram bitmap: 32 (32 Ki bits each, conflict-free), 16 (64 Ki bits,
-//              2-way bank conflicts) or 8 (128 Ki bits, ~2.7-way).  Fewer copies = fewer false positives.
+//   FK_COPIES  copies of the q-gram bitmap side by side in the 32 shared-memory banks; lane l probes copy
+//              l mod FK_COPIES, and a copy spans 32 / FK_COPIES banks (consecutive rows in consecutive banks),
+//              so the 32 / FK_COPIES lanes that share a copy spread over its banks by the low row bits:
+//              32 copies (32 Ki bits each) conflict-free, 16 (64 Ki bits) ~1.5 wavefronts per probe,
+//              8 -> ~2.1, 4 -> ~2.6, 2 (512 Ki bits) -> ~3.1.  Fewer copies = fewer false positives.
 //   FK_WB      "weak bit index": take the bit index from the low 5 bits of the multiplicative hash and
 //              form the address with IMAD (FMA pipe) -- one ALU-pipe instruction less per probe, at the
 //              price of a bit index that only depends on the q-gram's first byte.
+//   FK_S2      stride-2 probe for q = 4: ONE bitmap word answers "does a needle start at p" and "does a needle
+//              start at p + 1" for an even p.  The row is hashed from the three bytes the two q-grams share
+//              (text[p+1..p+4)); the bit is picked by the low 5 bits of the byte that is private to each
+//              (text[p] resp. text[p+4]).  Half the hashes / address computations / shared-memory loads per
+//              text byte; every needle inserts two cells.
+#ifndef FK_S2
+#define FK_S2 1
+#endif
 #ifndef FK_COPIES
-#define FK_COPIES 16
+#define FK_COPIES (FK_S2 ? 4 : 16)
 #endif
 #ifndef FK_WB
 #define FK_WB 1
 #endif
 constexpr int FILTER_COPIES = FK_COPIES;
-constexpr int FILTER_ROWBITS = FK_COPIES == 32 ? 10 : FK_COPIES == 16 ? 11 : 12;
+constexpr int FILTER_ROWBITS = FK_COPIES == 32 ? 10 : FK_COPIES == 16 ? 11 : FK_COPIES == 8 ? 12 : FK_COPIES == 4 ? 13 : FK_COPIES == 2 ? 14 : 15;
 constexpr int FILTER_ROWS_EFF = 1 << FILTER_ROWBITS;
 static_assert(FILTER_ROWS_EFF * FILTER_COPIES == FILTER_WORDS, "filter geometry");
 // Filter cell of a (masked) q-gram: row and bit 0..31.  Must match the device code.
@@ -127,6 +138,17 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
   *row = x >> (32 - FILTER_ROWBITS);
   const uint32_t s = FK_WB ? (x & 31u) : ((x >> 15) & 31u);
   *bit = 31u - s;   // the kernel rotates left by s and tests bit 31
+}
+// Stride-2 cells of a 4-gram g = n0 | n1 << 8 | n2 << 16 | n3 << 24 (FK_S2).  The kernel hashes the 4-gram X that
+// starts at p + 1 with HASH_MUL << 8, which drops X's top byte: the row depends on text[p+1..p+4) only.
+//   cell A (needle starts at the even position p):      row of (n1, n2, n3), bit chosen by n0
+//   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
+constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
+inline void filter_cells_s2(uint32_t g, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
+  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - FILTER_ROWBITS);
+  *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31
+  *row_b = (g * HASH_MUL_S2) >> (32 - FILTER_ROWBITS);
+  *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
 inline uint32_t t2_bucket(uint32_t g) { return (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS); }

@@ -11,6 +11,17 @@ namespace am {
 
 extern std::atomic<uint64_t> g_kernel_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
+// SM count of the current device (grids are sized as one persistent CTA, or two, per SM).
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 // Per-segment goto+failure walk (general path).  mode: ScanMode.
 cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);
 // q-gram filter + goto verify (fast path; requires A.q > 0 and CaseSensitive).
