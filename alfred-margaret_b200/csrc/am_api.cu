@@ -128,7 +128,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
   sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
   static const uint32_t dbg = []() { const char* e = std::getenv("AM_DEBUG_FLAGS"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-  sa.debug = dbg; sa.krow = 4u * FILTER_COPIES;
+  sa.debug = dbg; sa.krow = 4u * FILTER_COPIES; sa.rowmul = 1u << FILTER_ROWBITS;
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
@@ -280,9 +280,10 @@ int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_low
   std::memset(&D, 0, sizeof D);
   if (H.filter.empty()) { H.filter.assign(FILTER_WORDS, 0); }
   if (H.filter2.empty()) { H.filter2.assign(T2_WORDS, 0); }
-  if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE}); H.jump_mask = 15; }
+  if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE, 0, 0}); H.jump_mask = 15; }
+  if (H.tails.empty()) H.tails.assign(4, 0);
   if ((rc = upload(a, H.dense, &D.dense)) || (rc = upload(a, H.fail, &D.fail)) || (rc = upload(a, H.edges, &D.edges)) ||
-      (rc = upload(a, H.jump, &D.jump)) || (rc = upload(a, H.filter, &D.filter)) || (rc = upload(a, H.filter2, &D.filter2)) ||
+      (rc = upload(a, H.jump, &D.jump)) || (rc = upload(a, H.tails, &D.tails)) || (rc = upload(a, H.filter, &D.filter)) || (rc = upload(a, H.filter2, &D.filter2)) ||
       (rc = upload(a, H.own_off, &D.own_off)) || (rc = upload(a, H.own_rank, &D.own_rank)) ||
       (rc = upload(a, H.first_out, &D.first_out)) || (rc = upload(a, H.next_out, &D.next_out)) ||
       (rc = upload(a, H.chain_count, &D.chain_count)) || (rc = upload(a, H.id_of_rank, &D.id_of_rank)) ||

@@ -360,7 +360,8 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     A->filter_keys = (uint32_t)keys.size();
     A->filter.assign(FILTER_WORDS, 0);
     uint32_t cap = next_pow2((uint64_t)keys.size() * 2 + 16);
-    A->jump.assign(cap, JumpSlot{0, NONE});
+    A->jump.assign(cap, JumpSlot{0, NONE, 0, 0});
+    A->tails.clear();
     A->jump_mask = cap - 1;
     for (auto& kv : keys) {
       if (FK_S2 && q == 4) {   // stride-2 probe: one cell per parity of the start position
@@ -377,7 +378,30 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       }
       uint32_t i = jump_hash(kv.first) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
-      A->jump[i] = JumpSlot{kv.first, tagged(kv.second)};
+      JumpSlot slot{kv.first, tagged(kv.second), 0, 0};
+      {  // simple sub-trie?  follow the only child while the state holds no needle end
+        uint32_t t = kv.second;
+        std::vector<uint8_t> tail;
+        bool simple = true;
+        for (;;) {
+          const uint32_t nch = A->child_off[t + 1] - A->child_off[t];
+          const uint32_t nown = A->own_off[t + 1] - A->own_off[t];
+          if (nch == 0) { simple = nown > 0; break; }               // leaf
+          if (nch > 1 || nown > 0) { simple = false; break; }
+          tail.push_back(A->child_byte[A->child_off[t]]);
+          t = A->child_state[A->child_off[t]];
+        }
+        if (FK_TAIL && simple && tail.size() <= JUMP_TAIL_MASK) {
+          const uint32_t nown = A->own_off[t + 1] - A->own_off[t];
+          slot.tail_off = (uint32_t)A->tails.size();
+          slot.meta = JUMP_SIMPLE | (uint32_t)tail.size();
+          if (nown == 1) { slot.meta |= JUMP_SINGLE; slot.state = A->own_rank[A->own_off[t]]; }
+          else slot.state = t;
+          A->tails.insert(A->tails.end(), tail.begin(), tail.end());
+          while (A->tails.size() % 4) A->tails.push_back(0);
+        }
+      }
+      A->jump[i] = slot;
     }
     // second-level table (shared memory, 32 KiB): exact keys when they fit, else a bitmap
     A->t2_exact = keys.size() <= T2_MAX_EXACT_KEYS;

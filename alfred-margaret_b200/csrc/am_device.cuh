@@ -16,7 +16,8 @@ struct DevAutomaton {
   const uint32_t* dense;        // dense_states x 256 failure-resolved next states (tagged)
   const uint32_t* fail;         // per state
   const EdgeSlot* edges;        // hashed goto
-  const JumpSlot* jump;         // q-gram -> depth-q state
+  const JumpSlot* jump;         // q-gram -> depth-q state (+ the tail of a simple sub-trie)
+  const uint8_t* tails;         // tail bytes of the simple jump slots
   const uint32_t* filter;       // FILTER_WORDS words, bank-replicated q-gram bitmap
   const uint32_t* filter2;      // second-level q-gram bitmap
   const uint32_t* own_off;      // CSR of needles ending exactly at a state
@@ -47,6 +48,7 @@ struct ScanArgs {
   uint64_t cap;
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
+  uint32_t rowmul;              // filter rows per copy as a run-time value: the row is hi32(hash * rowmul), an IMAD.HI
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)
 };
 

@@ -4,6 +4,10 @@
 #include "am_device.cuh"
 #include "am_kernels.h"
 
+// The CTA's dynamic shared memory under an unmangled name, so that the kernel can take its shared-space address
+// with a plain `mov` (a compile-time constant) instead of converting a generic pointer.
+extern "C" { extern __shared__ __align__(128) unsigned char am_fk_smem[]; }
+
 namespace am {
 
 // =====================================================================================================
@@ -43,6 +47,14 @@ constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors 
 //   FK_DEBUG      compile the stage-isolation switches (AM_DEBUG_FLAGS=1: probes only, 2: no survivor walk)
 #ifndef FK_DEBUG
 #define FK_DEBUG 0
+#endif
+//   FK_HI         filter row from the hash with IMAD.HI (FMA pipe, half rate) instead of SHF (ALU pipe, the bottleneck)
+#ifndef FK_HI
+#define FK_HI 0
+#endif
+//   FK_OUTLINE    one out-of-line copy of the survivor drain per kernel instead of one per call site
+#ifndef FK_OUTLINE
+#define FK_OUTLINE 0
 #endif
 //   FK_LOOP2      second form of the main loop (pair loop unrolled by two, clamped instead of guarded loads)
 #ifndef FK_LOOP2
@@ -105,9 +117,43 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
   uint32_t idx = jump_hash(g) & A.jump_mask;
   uint32_t st;
   for (;;) {
-    const uint2 s = __ldg(reinterpret_cast<const uint2*>(A.jump) + idx);
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(A.jump) + idx);
     if (s.y == NONE) return;
-    if (s.x == g) { st = s.y; break; }
+    if (s.x == g) {
+#if FK_TAIL
+      if (s.w & JUMP_SIMPLE) {
+        // one needle path below this q-gram: compare its tail with the text in one go (independent loads)
+        const uint32_t tl = s.w & JUMP_TAIL_MASK;
+        const uint64_t end = i + A.q + tl;
+        if (end > a.text_len || end <= a.report_begin) return;
+        const uint8_t* tp = a.text + i + A.q;
+        const uint8_t* np = A.tails + s.z;
+        // four bytes per round (independent loads), leaving at the first round that differs: most survivors of a
+        // needle set too large for the exact second level are q-gram hits that fail within the first bytes
+        for (uint32_t k = 0; k < tl; k += 4) {
+          uint32_t diff = 0;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; j++)
+            if (k + j < tl) diff |= (uint32_t)__ldg(tp + k + j) ^ (uint32_t)__ldg(np + k + j);
+          if (diff) return;
+        }
+        if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
+        if (s.w & JUMP_SINGLE) {
+          if (MODE == MODE_COUNT) local_count += 1;
+          else fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | s.y);
+        } else {                                           // duplicates of one needle: all ranks of the leaf
+          const uint32_t olo = __ldg(A.own_off + s.y), ohi = __ldg(A.own_off + s.y + 1);
+          if (MODE == MODE_COUNT) local_count += ohi - olo;
+          else
+            for (uint32_t j = olo; j < ohi; j++)
+              fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+        }
+        return;
+      }
+#endif
+      st = s.y;                                            // not simple: the slot holds the depth-q state
+      break;
+    }
     idx = (idx + 1) & A.jump_mask;
   }
   uint32_t d = A.q;
@@ -146,14 +192,38 @@ __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanA
   if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
 }
 
+#if FK_OUTLINE
+// The drain is rare (once per ~60 KiB of text per warp) and large: keep ONE out-of-line copy per kernel instead of
+// one per call site, so the hot loop stays small.  The kernel parameters are __grid_constant__, so passing them by
+// reference does not force a local copy; the match count travels by value.
 template <int MODE>
-__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
+__device__ __noinline__ unsigned long long fk_drain_out(const DevAutomaton& A, const ScanArgs& a, uint64_t v_begin, uint32_t n) {
+  FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
+  unsigned long long cnt = 0;
+  fk_drain_body<MODE>(A, a, sm, FilterCtx(a, v_begin), cnt, n);
+  return cnt;
+}
+template <int MODE>
+__device__ __noinline__ unsigned long long fk_verify_out(const DevAutomaton& A, const ScanArgs& a, uint64_t v_begin, uint32_t rel, uint32_t g) {
+  FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
+  unsigned long long cnt = 0;
+  fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, cnt);
+  return cnt;
+}
+#endif
+
+template <int MODE>
+__device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint64_t v_begin,
                                          unsigned long long& local_count, uint32_t min_fill) {
   __syncwarp();
-  uint32_t n = sm->sq_n[c.warp];
+  uint32_t n = sm->sq_n[threadIdx.x >> 5];
   if (n > FK_SQ) n = FK_SQ;
   if (n < min_fill || n == 0) return;
-  fk_drain_body<MODE>(A, a, sm, c, local_count, n);
+#if FK_OUTLINE
+  local_count += fk_drain_out<MODE>(A, a, v_begin, n);
+#else
+  fk_drain_body<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, n);
+#endif
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -193,7 +263,15 @@ __device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmas
 // HASH_MUL << 8, which discards its top byte -- and the two bits are picked by rotating the word by text[p] and by
 // text[p + 4] (SHF uses the low 5 bits of the register, so any register whose low byte is that text byte serves).
 // Per two text bytes: 1.5 + 1 + 2 + 2 ALU-pipe instructions, 2 IMAD, 1 LDS (stride-1: 7.5, 4, 2).
-__device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t m,
+__device__ __forceinline__ uint32_t fk_row_addr(uint32_t y, uint32_t krow, uint32_t rowmul, uint32_t filt_lane) {
+#if FK_HI
+  return __umulhi(y, rowmul) * krow + filt_lane;             // IMAD.HI + IMAD: the row never touches the ALU pipe
+#else
+  return (y >> (32 - FILTER_ROWBITS)) * krow + filt_lane;    // SHF + IMAD
+#endif
+}
+
+__device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t rowmul, uint32_t m,
                                                   uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
   // h[k]: register whose low byte is text[4k + 2]
@@ -205,13 +283,13 @@ __device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t k
   for (int k = 3; k >= 0; k--) {
     {  // p = 4k + 2: positions 4k + 3 (cell B, private byte text[4k + 6]) and 4k + 2 (cell A, text[4k + 2])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 24) * HASH_MUL_S2;
-      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);
+      const uint32_t word = lds32(fk_row_addr(y, krow, rowmul, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, h[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, h[k]), m, 1);
     }
     {  // p = 4k: positions 4k + 1 (cell B, text[4k + 4]) and 4k (cell A, text[4k])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 8) * HASH_MUL_S2;
-      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);
+      const uint32_t word = lds32(fk_row_addr(y, krow, rowmul, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, w[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, w[k]), m, 1);
     }
@@ -232,14 +310,17 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
   *g_out = g;
   if (T2X) {
     uint32_t hb = (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS);
-    uint32_t aux;
-    for (;;) {
-      const uint4 b = lds128(t2_s + (hb << 4));
-      if (b.x == g) { aux = b.y; break; }
-      if (b.z == g) { aux = b.w; break; }
-      if (!(b.w & T2_AUX_OVERFLOW)) return false;          // the common exit: one probe
-      hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
+    uint4 b = lds128(t2_s + (hb << 4));
+    if (b.x != g && b.z != g) {
+      if (!(b.w & T2_AUX_OVERFLOW)) return false;          // the common exit: one probe, no key of this bucket matches
+      do {                                                 // the bucket overflowed at build time: the key may sit in a later one
+        hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
+        b = lds128(t2_s + (hb << 4));
+        if (b.x == g || b.z == g) break;
+      } while (b.w & T2_AUX_OVERFLOW);
+      if (b.x != g && b.z != g) return false;
     }
+    const uint32_t aux = b.x == g ? b.y : b.w;
     if (aux & T2_AUX_ANY) return true;
     uint32_t nb;                                           // text byte right after the q-gram
     if (Q4) nb = (hi >> sh) & 0xFFu;
@@ -252,9 +333,8 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
 }
 
 template <int MODE, bool Q4, bool T2X>
-__global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  FilterSmem* sm = reinterpret_cast<FilterSmem*>(smem_raw);
+__global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_constant__ DevAutomaton A, const __grid_constant__ ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
+  FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // ---- stage the filter bitmap and T2 into shared memory with TMA bulk copies -----------------------
@@ -295,7 +375,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
   const uint32_t a0 = (uint32_t)(addr0 & 15);
   const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
   const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text (>= 1 here)
-  const uint32_t smem0 = smem_u32(smem_raw);
+  uint32_t smem0;
+  asm("mov.u32 %0, am_fk_smem;" : "=r"(smem0));
   const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & (FK_COPIES - 1u)) << 2);
   const uint32_t win_s = smem0 + (uint32_t)offsetof(FilterSmem, window) + warp * (FK_WIN_WORDS * 4u);
   const uint32_t win_lane = win_s + (lane << 4);
@@ -326,8 +407,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
     const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail : qb.x, (lane + 1) & 31);
     uint32_t m = 0;                                        // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
     if (Q4 && FK_S2) {
-      m = fk_probe16_s2(filt_lane, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
-      m = fk_probe16_s2(filt_lane, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
+      m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, qb.x, qb.y, qb.z, qb.w, w4B);
+      m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, qa.x, qa.y, qa.z, qa.w, w4A);
     } else {
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
@@ -350,10 +431,14 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
         const uint32_t rel = pair_rel + o + (lane << 4);
         const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
         if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(rel, g);
+#if FK_OUTLINE
+        else local_count += fk_verify_out<MODE>(A, a, v_begin, rel, g);                      // queue full: verify in place
+#else
         else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
+#endif
       }
     }
-    fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
+    fk_drain<MODE>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
   };
 
   static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
@@ -445,8 +530,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
       const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail_cur : cB.x, (lane + 1) & 31);
       uint32_t m = 0;                                      // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
       if (Q4 && FK_S2) {
-        m = fk_probe16_s2(filt_lane, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
-        m = fk_probe16_s2(filt_lane, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
+        m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, cB.x, cB.y, cB.z, cB.w, w4B);
+        m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, cA.x, cA.y, cA.z, cA.w, w4A);
       } else {
         m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
         m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
@@ -471,12 +556,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(DevAutomaton A, S
           else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), pair_rel + o, g, local_count);   // queue full: verify in place
         }
       }
-      fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
+      fk_drain<MODE>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
       cA = nA; cB = nB; tail_cur = tail_next;
     }
   }
 #endif
-  fk_drain<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, 1);
+  fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
   if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
 
   if (MODE == MODE_COUNT) {

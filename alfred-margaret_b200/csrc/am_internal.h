@@ -44,7 +44,14 @@ constexpr uint32_t LOWER_BLOCK_SHIFT = 7;    // two-stage lower-case table: 128 
 constexpr uint32_t LOWER_STAGE1 = 0x110000 >> LOWER_BLOCK_SHIFT;
 
 struct EdgeSlot { uint32_t key_lo, key_hi, child, pad; };   // key = state << 8 | byte ; child carries OUT_FLAG
-struct JumpSlot { uint32_t key, state; };                    // state == NONE => empty ; state carries OUT_FLAG
+// Jump table slot: q-gram -> trie state at depth q (state == NONE => empty; state carries the flags).  When the
+// sub-trie below that state is a single path that ends in a leaf and holds no other needle end ("simple": true for
+// nearly every q-gram of a random needle set), the slot also carries the path: `meta` = JUMP_SIMPLE | tail length,
+// `tail_off` = offset of the tail bytes in HostAutomaton::tails (4-byte aligned), and `state` = the LEAF's state --
+// or, with JUMP_SINGLE (one needle ends there), directly that needle's rank.  The survivor check is then one
+// byte-wise comparison whose loads are all independent, instead of one dependent hashed edge lookup per byte.
+struct JumpSlot { uint32_t key, state, tail_off, meta; };
+constexpr uint32_t JUMP_SIMPLE = 0x80000000u, JUMP_SINGLE = 0x40000000u, JUMP_TAIL_MASK = 0xFFFFu;
 
 inline uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x;
@@ -94,6 +101,7 @@ struct HostAutomaton {
   std::vector<uint32_t> cdfa;
   std::vector<EdgeSlot> edges; uint32_t edge_mask = 0;
   std::vector<JumpSlot> jump; uint32_t jump_mask = 0;
+  std::vector<uint8_t> tails;                   // tail bytes of the simple jump slots
   std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated
   std::vector<uint32_t> filter2;                // T2_WORDS: bitmap, or exact key buckets when t2_exact
   uint32_t t2_exact = 0, t2_empty_key = 0xFFFFFFFFu;
@@ -119,11 +127,16 @@ inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (
 //              (text[p+1..p+4)); the bit is picked by the low 5 bits of the byte that is private to each
 //              (text[p] resp. text[p+4]).  Half the hashes / address computations / shared-memory loads per
 //              text byte; every needle inserts two cells.
+//   FK_TAIL    survivors whose q-gram leads into a single needle path are checked by one tail comparison
+//              (JumpSlot) instead of a walk through the hashed goto table.
 #ifndef FK_S2
 #define FK_S2 1
 #endif
+#ifndef FK_TAIL
+#define FK_TAIL 1
+#endif
 #ifndef FK_COPIES
-#define FK_COPIES (FK_S2 ? 4 : 16)
+#define FK_COPIES (FK_S2 ? 2 : 16)
 #endif
 #ifndef FK_WB
 #define FK_WB 1

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/ab.log 2>&1
 ( timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) >> gpurun_out/ab.log 2>&1
-for v in ${VARIANTS:-base _c2 _c8 _c16 _s1 _old}; do
+for v in ${VARIANTS:-base _c2 _c1 _c2hi _c1hi _c2nt _c2ol}; do
   [ "$v" = "base" ] && v=""
   export AM_LIB=$PWD/alfred-margaret_b200/lib/libam_b200$v.so
   echo "=== variant '$v'" >> gpurun_out/ab.log
