@@ -70,6 +70,7 @@ SYMBOLS = {
     "am_replacer_free": (None, [C.c_void_p]),
     "am_replacer_run": (C.c_int, [C.c_void_p, U8Slice, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "am_replacer_last_passes": (C.c_uint64, []),
+    "am_replacer_last_rescans": (C.c_uint64, []),
     "am_free": (None, [C.c_void_p]),
     "am_lower_utf8": (C.c_int, [C.POINTER(LowerTable), U8Slice, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
     "am_skip_code_points_backwards": (C.c_int, [U8Slice, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),

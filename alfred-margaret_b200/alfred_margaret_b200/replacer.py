@@ -28,6 +28,7 @@ class Replacer:
                                                 self._lower.ptr(), C.byref(opts), C.byref(h)))
         self.handle = h
         self.last_passes = 0
+        self.last_rescans = 0   # passes that scanned the whole text (1 when the match list is carried between passes)
 
     @staticmethod
     def _b(x) -> bytes:
@@ -81,6 +82,7 @@ def run_with_limit(r: Replacer, max_length: int, text) -> Optional[bytes]:
     out, out_len, exceeded = C.c_void_p(), C.c_uint64(), C.c_int()
     _ffi.check(_ffi.lib().am_replacer_run(r.handle, t.slice(), max_length, C.byref(out), C.byref(out_len), C.byref(exceeded)))
     r.last_passes = _ffi.lib().am_replacer_last_passes()
+    r.last_rescans = _ffi.lib().am_replacer_last_rescans()
     if exceeded.value:
         return None
     n = out_len.value

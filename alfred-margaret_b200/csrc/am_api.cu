@@ -19,7 +19,7 @@
 namespace am {
 
 thread_local std::string g_last_error;
-thread_local uint64_t g_last_passes = 0;
+thread_local uint64_t g_last_passes = 0, g_last_rescans = 0;
 std::atomic<uint64_t> g_kernel_launches{0};
 static std::atomic<int> g_profile{0};
 thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -114,7 +114,6 @@ int check_ready(const am_automaton* a) {
   return AM_OK;
 }
 
-static int bitlen(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
 
 // Launch one scan in `mode`; COUNT/EMIT totals land in ws->d_scalars[0], the ANY flag in d_scalars[8..].
 int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st) {
@@ -128,7 +127,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
   sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
   static const uint32_t dbg = []() { const char* e = std::getenv("AM_DEBUG_FLAGS"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-  sa.debug = dbg; sa.krow = 4u * FILTER_COPIES; sa.rowmul = 1u << FILTER_ROWBITS;
+  sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q);
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
@@ -523,6 +522,7 @@ int am_profile_last_scan_ms(float* ms) {
 }
 uint64_t am_profile_kernel_launches(void) { return g_kernel_launches.load(); }
 uint64_t am_replacer_last_passes(void) { return g_last_passes; }
+uint64_t am_replacer_last_rescans(void) { return g_last_rescans; }
 
 // ---- synthetic workloads ----------------------------------------------------------------------------------------------
 int am_synth_fill_dev(void* dev_buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* alphabet, uint32_t alphabet_len, void* stream) {

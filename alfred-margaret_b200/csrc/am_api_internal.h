@@ -32,7 +32,8 @@ struct Workspace {
 };
 
 extern thread_local std::string g_last_error;
-extern thread_local uint64_t g_last_passes;
+extern thread_local uint64_t g_last_passes, g_last_rescans;
+inline int bitlen(uint64_t x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
 int fail(int code, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 int check_ready(const struct ::am_automaton* a);

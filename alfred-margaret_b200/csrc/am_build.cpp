@@ -364,17 +364,18 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     A->tails.clear();
     A->jump_mask = cap - 1;
     for (auto& kv : keys) {
-      if (FK_S2 && q == 4) {   // stride-2 probe: one cell per parity of the start position
+      const int copies = filter_copies(q);
+      if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
         uint32_t ra, ba, rb, bb;
         filter_cells_s2(kv.first, &ra, &ba, &rb, &bb);
-        for (int c = 0; c < FILTER_COPIES; c++) {
-          A->filter[(size_t)ra * FILTER_COPIES + c] |= 1u << ba;
-          A->filter[(size_t)rb * FILTER_COPIES + c] |= 1u << bb;
+        for (int c = 0; c < copies; c++) {
+          A->filter[(size_t)ra * copies + c] |= 1u << ba;
+          A->filter[(size_t)rb * copies + c] |= 1u << bb;
         }
       } else {
         uint32_t row, bit;
         filter_cell(kv.first, &row, &bit);
-        for (int c = 0; c < FILTER_COPIES; c++) A->filter[(size_t)row * FILTER_COPIES + c] |= 1u << bit;
+        for (int c = 0; c < copies; c++) A->filter[(size_t)row * copies + c] |= 1u << bit;
       }
       uint32_t i = jump_hash(kv.first) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;

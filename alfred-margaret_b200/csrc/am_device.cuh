@@ -48,7 +48,6 @@ struct ScanArgs {
   uint64_t cap;
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
-  uint32_t rowmul;              // filter rows per copy as a run-time value: the row is hi32(hash * rowmul), an IMAD.HI
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)
 };
 

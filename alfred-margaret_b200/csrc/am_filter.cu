@@ -16,7 +16,8 @@ namespace am {
 // Per warp, per 4 KiB chunk, in pairs of 512-byte iterations:
 //   1. stream two 16-byte granules per lane from HBM (next pair prefetched into registers) and mirror
 //      them into the warp's 1 KiB shared-memory window;
-//   2. probe the bank-private q-gram bitmap once per text position (32 candidate bits per lane);
+//   2. probe the q-gram bitmap in shared memory: one probe per TWO text positions for q = 4 (stride-2 cells,
+//      fk_probe16_s2), one per position for shorter q-grams (32 candidate bits per lane either way);
 //   3. pop the candidate bits: re-read the exact q-gram from the window, test it against the exact
 //      second-level table T2 (shared memory) -> "survivors" (true q-gram prefix hits, ~0.2 %);
 //   4. survivors are queued per warp and, 32 at a time, walked through the goto trie in HBM/L2
@@ -37,28 +38,11 @@ constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail wo
 constexpr int FK_SQ = 64;                        // survivor queue entries per warp
 constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
 constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
-// Build-time variants (A/B-tested on the GPU):
-//   (a warp-scan "dense" compaction of the candidates was A/B-tested and was not faster; removed)
-//   FK_PF         distance (in CTA tiles) of the bulk L2 prefetch issued ahead of the streaming loads; the
-//                 register double-buffer alone keeps too few bytes in flight to cover HBM latency
-#ifndef FK_PF
-#define FK_PF 0
-#endif
+// Build-time variants (A/B-tested on the GPU; the rejected ones -- warp-scan compaction of the candidates, bulk L2
+// prefetch, IMAD.HI row addressing, an out-of-line survivor drain -- are recorded in profiles/README.md):
 //   FK_DEBUG      compile the stage-isolation switches (AM_DEBUG_FLAGS=1: probes only, 2: no survivor walk)
 #ifndef FK_DEBUG
 #define FK_DEBUG 0
-#endif
-//   FK_HI         filter row from the hash with IMAD.HI (FMA pipe, half rate) instead of SHF (ALU pipe, the bottleneck)
-#ifndef FK_HI
-#define FK_HI 0
-#endif
-//   FK_OUTLINE    one out-of-line copy of the survivor drain per kernel instead of one per call site
-#ifndef FK_OUTLINE
-#define FK_OUTLINE 0
-#endif
-//   FK_LOOP2      second form of the main loop (pair loop unrolled by two, clamped instead of guarded loads)
-#ifndef FK_LOOP2
-#define FK_LOOP2 1
 #endif
 
 struct FilterSmem {
@@ -192,25 +176,6 @@ __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanA
   if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
 }
 
-#if FK_OUTLINE
-// The drain is rare (once per ~60 KiB of text per warp) and large: keep ONE out-of-line copy per kernel instead of
-// one per call site, so the hot loop stays small.  The kernel parameters are __grid_constant__, so passing them by
-// reference does not force a local copy; the match count travels by value.
-template <int MODE>
-__device__ __noinline__ unsigned long long fk_drain_out(const DevAutomaton& A, const ScanArgs& a, uint64_t v_begin, uint32_t n) {
-  FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
-  unsigned long long cnt = 0;
-  fk_drain_body<MODE>(A, a, sm, FilterCtx(a, v_begin), cnt, n);
-  return cnt;
-}
-template <int MODE>
-__device__ __noinline__ unsigned long long fk_verify_out(const DevAutomaton& A, const ScanArgs& a, uint64_t v_begin, uint32_t rel, uint32_t g) {
-  FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
-  unsigned long long cnt = 0;
-  fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, cnt);
-  return cnt;
-}
-#endif
 
 template <int MODE>
 __device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint64_t v_begin,
@@ -219,11 +184,7 @@ __device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& 
   uint32_t n = sm->sq_n[threadIdx.x >> 5];
   if (n > FK_SQ) n = FK_SQ;
   if (n < min_fill || n == 0) return;
-#if FK_OUTLINE
-  local_count += fk_drain_out<MODE>(A, a, v_begin, n);
-#else
   fk_drain_body<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, n);
-#endif
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -246,10 +207,10 @@ __device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmas
       if (!Q4) g &= qmask;
 #if FK_WB
       const uint32_t y = g * HASH_MUL;                     // bit index = low 5 bits, row = top bits
-      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS)) * krow + filt_lane);   // SHF + IMAD(UR) + LDS
+      const uint32_t word = lds32((y >> (32 - FILTER_ROWBITS_S1)) * krow + filt_lane);   // SHF + IMAD(UR) + LDS
 #else
-      const uint32_t y = (g * HASH_MUL) >> 15;             // bits 0..4 bit index, top FILTER_ROWBITS bits row
-      const uint32_t word = lds32((y & (((1u << FILTER_ROWBITS) - 1u) << (17 - FILTER_ROWBITS))) + filt_lane);
+      const uint32_t y = (g * HASH_MUL) >> 15;             // bits 0..4 bit index, top FILTER_ROWBITS_S1 bits row
+      const uint32_t word = lds32((y & (((1u << FILTER_ROWBITS_S1) - 1u) << (17 - FILTER_ROWBITS_S1))) + filt_lane);
 #endif
       const uint32_t t = __funnelshift_l(word, word, y);   // rotate the tested bit into bit 31
       m = __funnelshift_l(t, m, 1);                        // m = m << 1 | t >> 31
@@ -263,15 +224,11 @@ __device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmas
 // HASH_MUL << 8, which discards its top byte -- and the two bits are picked by rotating the word by text[p] and by
 // text[p + 4] (SHF uses the low 5 bits of the register, so any register whose low byte is that text byte serves).
 // Per two text bytes: 1.5 + 1 + 2 + 2 ALU-pipe instructions, 2 IMAD, 1 LDS (stride-1: 7.5, 4, 2).
-__device__ __forceinline__ uint32_t fk_row_addr(uint32_t y, uint32_t krow, uint32_t rowmul, uint32_t filt_lane) {
-#if FK_HI
-  return __umulhi(y, rowmul) * krow + filt_lane;             // IMAD.HI + IMAD: the row never touches the ALU pipe
-#else
-  return (y >> (32 - FILTER_ROWBITS)) * krow + filt_lane;    // SHF + IMAD
-#endif
+__device__ __forceinline__ uint32_t fk_row_addr(uint32_t y, uint32_t krow, uint32_t filt_lane) {
+  return (y >> (32 - FILTER_ROWBITS_S2)) * krow + filt_lane;   // SHF + IMAD (krow is a run-time value: keeps the address an IMAD)
 }
 
-__device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t rowmul, uint32_t m,
+__device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t m,
                                                   uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
   // h[k]: register whose low byte is text[4k + 2]
@@ -283,13 +240,13 @@ __device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t k
   for (int k = 3; k >= 0; k--) {
     {  // p = 4k + 2: positions 4k + 3 (cell B, private byte text[4k + 6]) and 4k + 2 (cell A, text[4k + 2])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 24) * HASH_MUL_S2;
-      const uint32_t word = lds32(fk_row_addr(y, krow, rowmul, filt_lane));
+      const uint32_t word = lds32(fk_row_addr(y, krow, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, h[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, h[k]), m, 1);
     }
     {  // p = 4k: positions 4k + 1 (cell B, text[4k + 4]) and 4k (cell A, text[4k])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 8) * HASH_MUL_S2;
-      const uint32_t word = lds32(fk_row_addr(y, krow, rowmul, filt_lane));
+      const uint32_t word = lds32(fk_row_addr(y, krow, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, w[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, w[k]), m, 1);
     }
@@ -364,10 +321,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
                    : "=r"(done) : "r"(smem_u32(&sm->mbar)), "r"(0u) : "memory");
   }
 
-#if FK_LOOP2
-  // ---- main loop, second form ------------------------------------------------------------------------------------
-  // Same pipeline (everything a pair needs was requested one pair earlier), restated so that the hot path carries
-  // no bookkeeping: the pair loop is unrolled by two (register ping-pong instead of moves), the position of the next
+  // ---- main loop ---------------------------------------------------------------------------------------------------
+  // Software pipeline over (tile, pair): everything a pair needs -- its two granules per lane and the word that
+  // follows the pair -- was requested one pair earlier, including across chunk and tile boundaries.  The hot path
+  // carries no bookkeeping: the pair loop is unrolled by two (register ping-pong instead of moves), the position of the next
   // pair is one warp-uniform granule index, loads that could leave the text are CLAMPED to its last granule instead
   // of being guarded (bytes beyond the text only ever reach candidates that the exact verification rejects on
   // bounds), shared-memory addresses are compile-time offsets from the CTA's dynamic shared memory base.
@@ -377,7 +334,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text (>= 1 here)
   uint32_t smem0;
   asm("mov.u32 %0, am_fk_smem;" : "=r"(smem0));
-  const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & (FK_COPIES - 1u)) << 2);
+  const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & ((Q4 && FK_S2 ? FK_COPIES_S2 : FK_COPIES_S1) - 1u)) << 2);
   const uint32_t win_s = smem0 + (uint32_t)offsetof(FilterSmem, window) + warp * (FK_WIN_WORDS * 4u);
   const uint32_t win_lane = win_s + (lane << 4);
   const uint32_t t2_s = smem0 + (uint32_t)offsetof(FilterSmem, t2);
@@ -407,8 +364,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
     const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail : qb.x, (lane + 1) & 31);
     uint32_t m = 0;                                        // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
     if (Q4 && FK_S2) {
-      m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, qb.x, qb.y, qb.z, qb.w, w4B);
-      m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, qa.x, qa.y, qa.z, qa.w, w4A);
+      m = fk_probe16_s2(filt_lane, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
+      m = fk_probe16_s2(filt_lane, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
     } else {
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
@@ -431,11 +388,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
         const uint32_t rel = pair_rel + o + (lane << 4);
         const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
         if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(rel, g);
-#if FK_OUTLINE
-        else local_count += fk_verify_out<MODE>(A, a, v_begin, rel, g);                      // queue full: verify in place
-#else
         else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
-#endif
       }
     }
     fk_drain<MODE>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
@@ -460,107 +413,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       process_pair(nA, nB, tN, chunk_rel + (uint32_t)pair * 1024u + 1024u);
     }
   }
-#else
-
-  const uintptr_t addr0 = reinterpret_cast<uintptr_t>(a.text);
-  const uint32_t a0 = (uint32_t)(addr0 & 15);
-  const uint4* base16 = reinterpret_cast<const uint4*>(addr0 - a0);
-  const uint32_t* base32 = reinterpret_cast<const uint32_t*>(base16);
-  const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text
-  const uint32_t filt_lane = smem_u32(sm->filter) + ((lane & (FK_COPIES - 1u)) << 2);   // this lane's private copy (bank)
-  uint32_t* win = sm->window[warp];
-  const uint32_t win_s = smem_u32(win), t2_s = smem_u32(sm->t2);
-  unsigned long long local_count = 0;
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
-
-  // Software pipeline over (tile, pair): everything a pair needs was requested one pair earlier -- its two
-  // granules per lane and the word that follows the pair -- including across chunk and tile boundaries.
-  // Interior tiles (everything they and their successor's first pair touch lies inside the text) use
-  // unguarded loads at immediate offsets from one per-lane pointer; edge tiles take the guarded path.
-  auto pair_granule = [&](uint64_t tile, int pair) -> uint64_t {   // first 16-byte granule of (tile, pair) for this warp
-    return ((v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK) >> 4) + (uint64_t)pair * 64;
-  };
-  auto load_pair_guarded = [&](uint64_t g, uint4& A, uint4& B, uint32_t& tail) {
-    A = zero4; B = zero4; tail = 0;
-    if (g + lane < nvec) A = ld_stream_v4(base16 + g + lane);
-    if (g + 32 + lane < nvec) B = ld_stream_v4(base16 + g + 32 + lane);
-    if (lane == 0 && g + 64 < nvec) tail = __ldg(base32 + (g + 64) * 4);
-  };
-  uint4 cA = zero4, cB = zero4;
-  uint32_t tail_cur = 0;
-  if (blockIdx.x < num_tiles) load_pair_guarded(pair_granule(blockIdx.x, 0), cA, cB, tail_cur);
-  const uint64_t tile_stride_granules = (uint64_t)gridDim.x * (FK_TILE / 16);
-  for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
-    const uint64_t chunk_v0 = v_begin + tile * FK_TILE + (uint64_t)warp * FK_CHUNK;  // granule-aligned virtual index
-    const uint32_t chunk_rel = (uint32_t)(chunk_v0 - v_begin);
-    const uint64_t g0 = chunk_v0 >> 4;
-    const bool has_next = tile + gridDim.x < num_tiles;
-    // last granule touched from this tile: the tail word of the NEXT tile's first pair (or of our last pair)
-    const bool interior = (has_next ? g0 + tile_stride_granules + 64 + 1 : g0 + FK_PAIRS * 64 + 1) < nvec;
-    const uint4* pl = base16 + g0 + lane;
-#if FK_PF > 0
-    if (lane == 0) {   // pull this warp's chunk of a later tile into L2 (one TMA-style bulk prefetch, no registers)
-      const uint64_t pv = g0 + (uint64_t)FK_PF * tile_stride_granules;
-      if (tile + (uint64_t)FK_PF * gridDim.x < num_tiles && pv + FK_CHUNK / 16 <= nvec)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base16 + pv), "r"((uint32_t)FK_CHUNK) : "memory");
-    }
-#endif
-#pragma unroll 1
-    for (int pair = 0; pair < FK_PAIRS; pair++) {
-      // request the next pair (same chunk, or the first pair of this warp's chunk in the CTA's next tile)
-      uint4 nA = zero4, nB = zero4;
-      uint32_t tail_next = 0;
-      const bool same = pair + 1 < FK_PAIRS;
-      if (interior) {
-        if (same || has_next) {
-          const uint4* pn = same ? pl + 64 * (pair + 1) : pl + tile_stride_granules;   // this lane's granule of the NEXT pair
-          nA = ld_stream_v4(pn);
-          nB = ld_stream_v4(pn + 32);
-          if (lane == 0) tail_next = __ldg(reinterpret_cast<const uint32_t*>(pn + 64));
-        }
-      } else if (same || has_next) {
-        load_pair_guarded(pair_granule(same ? tile : tile + gridDim.x, same ? pair + 1 : 0), nA, nB, tail_next);
-      }
-      // mirror the pair into the window (exact q-gram recovery for the few candidates)
-      reinterpret_cast<uint4*>(win)[lane] = cA;
-      reinterpret_cast<uint4*>(win)[32 + lane] = cB;
-      if (lane == 0) win[256] = tail_cur;
-      const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? cB.x : cA.x, (lane + 1) & 31);
-      const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail_cur : cB.x, (lane + 1) & 31);
-      uint32_t m = 0;                                      // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
-      if (Q4 && FK_S2) {
-        m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, cB.x, cB.y, cB.z, cB.w, w4B);
-        m = fk_probe16_s2(filt_lane, a.krow, a.rowmul, m, cA.x, cA.y, cA.z, cA.w, w4A);
-      } else {
-        m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cB.x, cB.y, cB.z, cB.w, w4B);
-        m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, cA.x, cA.y, cA.z, cA.w, w4A);
-      }
-      __syncwarp();
-#if FK_DEBUG
-      if (a.debug & 1u) { local_count += __popc(m); m = 0; }
-#endif
-      const uint32_t pair_rel = chunk_rel + (uint32_t)pair * 1024u;
-      // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
-      while (m) {
-        const uint32_t P = 31u - __clz(m);                    // FLO: highest candidate position
-        m ^= 1u << P;
-        const uint32_t o = (P & 16u) * 31u + P + (lane << 4);  // byte offset inside the pair: (P >> 4) * 512 + lane * 16 + (P & 15)
-        uint32_t g;
-        if (fk_phase_a<Q4, T2X>(A, win_s, t2_s, o, &g)) {
-#if FK_DEBUG
-          if (a.debug & 2u) { local_count++; continue; }
-#endif
-          const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-          if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(pair_rel + o, g);
-          else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), pair_rel + o, g, local_count);   // queue full: verify in place
-        }
-      }
-      fk_drain<MODE>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
-      cA = nA; cB = nB; tail_cur = tail_next;
-    }
-  }
-#endif
   fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
   if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
 

@@ -114,41 +114,47 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
 
 inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
 // Build-time variants of the filter kernel (A/B-tested on the GPU):
-//   FK_COPIES  copies of the q-gram bitmap side by side in the 32 shared-memory banks; lane l probes copy
-//              l mod FK_COPIES, and a copy spans 32 / FK_COPIES banks (consecutive rows in consecutive banks),
-//              so the 32 / FK_COPIES lanes that share a copy spread over its banks by the low row bits:
-//              32 copies (32 Ki bits each) conflict-free, 16 (64 Ki bits) ~1.5 wavefronts per probe,
-//              8 -> ~2.1, 4 -> ~2.6, 2 (512 Ki bits) -> ~3.1.  Fewer copies = fewer false positives.
-//   FK_WB      "weak bit index": take the bit index from the low 5 bits of the multiplicative hash and
-//              form the address with IMAD (FMA pipe) -- one ALU-pipe instruction less per probe, at the
-//              price of a bit index that only depends on the q-gram's first byte.
-//   FK_S2      stride-2 probe for q = 4: ONE bitmap word answers "does a needle start at p" and "does a needle
-//              start at p + 1" for an even p.  The row is hashed from the three bytes the two q-grams share
-//              (text[p+1..p+4)); the bit is picked by the low 5 bits of the byte that is private to each
-//              (text[p] resp. text[p+4]).  Half the hashes / address computations / shared-memory loads per
-//              text byte; every needle inserts two cells.
-//   FK_TAIL    survivors whose q-gram leads into a single needle path are checked by one tail comparison
-//              (JumpSlot) instead of a walk through the hashed goto table.
+//   FK_S2         stride-2 probe for q = 4: ONE bitmap word answers "does a needle start at p" and "does a needle
+//                 start at p + 1" for an even p.  The row is hashed from the three bytes the two q-grams share
+//                 (text[p+1..p+4)); the bit is picked by the low 5 bits of the byte that is private to each
+//                 (text[p] resp. text[p+4]).  Half the hashes / address computations / shared-memory loads per
+//                 text byte; every needle inserts two cells.
+//   FK_COPIES_S2, copies of the q-gram bitmap side by side in the 32 shared-memory banks, for the stride-2 and the
+//   FK_COPIES_S1  stride-1 (q < 4) probe.  Lane l probes copy l mod COPIES, and a copy spans 32 / COPIES banks
+//                 (consecutive rows in consecutive banks), so the lanes that share a copy spread over its banks by
+//                 the low row bits: 32 copies (32 Ki bits each) are conflict-free, 16 (64 Ki bits) cost ~1.5
+//                 wavefronts per probe, 8 -> ~2.1, 4 -> ~2.6, 2 (512 Ki bits) -> ~3.1, 1 -> ~3.5.  Fewer copies =
+//                 fewer false positives.  The stride-2 probe issues half the loads, so it affords 2 copies
+//                 (measured best: 16/8/4/2/1 copies -> 1.93/1.72/1.63/1.57/1.50* ms per 4 GiB; *with later changes
+//                 1 copy was 1 % slower than 2); the stride-1 probe stays at 16.
+//   FK_WB         stride-1 probe: take the bit index from the low 5 bits of the multiplicative hash and form the
+//                 address with IMAD (FMA pipe) -- one ALU-pipe instruction less per probe.
+//   FK_TAIL       survivors whose q-gram leads into a single needle path are checked by one tail comparison
+//                 (JumpSlot) instead of a walk through the hashed goto table.
 #ifndef FK_S2
 #define FK_S2 1
 #endif
 #ifndef FK_TAIL
 #define FK_TAIL 1
 #endif
-#ifndef FK_COPIES
-#define FK_COPIES (FK_S2 ? 2 : 16)
+#ifndef FK_COPIES_S2
+#define FK_COPIES_S2 2
+#endif
+#ifndef FK_COPIES_S1
+#define FK_COPIES_S1 16
 #endif
 #ifndef FK_WB
 #define FK_WB 1
 #endif
-constexpr int FILTER_COPIES = FK_COPIES;
-constexpr int FILTER_ROWBITS = FK_COPIES == 32 ? 10 : FK_COPIES == 16 ? 11 : FK_COPIES == 8 ? 12 : FK_COPIES == 4 ? 13 : FK_COPIES == 2 ? 14 : 15;
-constexpr int FILTER_ROWS_EFF = 1 << FILTER_ROWBITS;
-static_assert(FILTER_ROWS_EFF * FILTER_COPIES == FILTER_WORDS, "filter geometry");
+constexpr int filter_rowbits(int copies) { return copies == 32 ? 10 : copies == 16 ? 11 : copies == 8 ? 12 : copies == 4 ? 13 : copies == 2 ? 14 : 15; }
+constexpr int FILTER_ROWBITS_S2 = filter_rowbits(FK_COPIES_S2), FILTER_ROWBITS_S1 = filter_rowbits(FK_COPIES_S1);
+static_assert((1 << FILTER_ROWBITS_S2) * FK_COPIES_S2 == FILTER_WORDS && (1 << FILTER_ROWBITS_S1) * FK_COPIES_S1 == FILTER_WORDS, "filter geometry");
+inline bool filter_is_s2(uint32_t q) { return FK_S2 && q == 4; }
+inline int filter_copies(uint32_t q) { return filter_is_s2(q) ? FK_COPIES_S2 : FK_COPIES_S1; }
 // Filter cell of a (masked) q-gram: row and bit 0..31.  Must match the device code.
 inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
   const uint32_t x = g * HASH_MUL;
-  *row = x >> (32 - FILTER_ROWBITS);
+  *row = x >> (32 - FILTER_ROWBITS_S1);
   const uint32_t s = FK_WB ? (x & 31u) : ((x >> 15) & 31u);
   *bit = 31u - s;   // the kernel rotates left by s and tests bit 31
 }
@@ -158,9 +164,9 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
 //   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
 constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
 inline void filter_cells_s2(uint32_t g, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
-  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - FILTER_ROWBITS);
+  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - FILTER_ROWBITS_S2);
   *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31
-  *row_b = (g * HASH_MUL_S2) >> (32 - FILTER_ROWBITS);
+  *row_b = (g * HASH_MUL_S2) >> (32 - FILTER_ROWBITS_S2);
   *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }

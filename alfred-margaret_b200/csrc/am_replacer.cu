@@ -121,8 +121,20 @@ __global__ void gather_kept_kernel(const uint64_t* start, const uint64_t* end, c
 // The CTA that owns a match's first byte (or, for an empty match, its position) writes the replacement.
 constexpr int SPLICE_TILE = 1 << 16;
 
-// CTA-cooperative copy of n bytes with arbitrary relative misalignment: 16-byte aligned stores, the source is
-// read as aligned 32-bit words and re-aligned with funnel shifts.
+// CTA-cooperative copy of n bytes with arbitrary relative misalignment: 16-byte aligned stores; the source is read
+// as aligned 16-byte vectors (vector i + 1 is the next thread's vector i: served by L1) and re-aligned with funnel
+// shifts.  May read up to 31 bytes beyond s + n (every text buffer carries 64 bytes of slack).
+template <int WS>
+__device__ __forceinline__ uint4 splice_realign(const uint4& a, const uint4& b, uint32_t bs) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  return make_uint4(__funnelshift_r(w[WS], w[WS + 1], bs), __funnelshift_r(w[WS + 1], w[WS + 2], bs),
+                    __funnelshift_r(w[WS + 2], w[WS + 3], bs), __funnelshift_r(w[WS + 3], w[WS + 4], bs));
+}
+template <int WS>
+__device__ __forceinline__ void splice_copy_vec(uint4* dv, const uint4* sv, uint64_t nvec, uint32_t bs) {
+#pragma unroll 2
+  for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) dv[i] = splice_realign<WS>(__ldg(sv + i), __ldg(sv + i + 1), bs);
+}
 __device__ __forceinline__ void splice_copy(uint8_t* d, const uint8_t* s, uint64_t n) {
   // head: bytes until d is 16-byte aligned
   uint64_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
@@ -130,20 +142,19 @@ __device__ __forceinline__ void splice_copy(uint8_t* d, const uint8_t* s, uint64
   for (uint64_t x = threadIdx.x; x < head; x += blockDim.x) d[x] = s[x];
   d += head; s += head; n -= head;
   const uint64_t nvec = n >> 4;
-  const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3);
-  const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - r);   // aligned words; word i covers source bytes [4i - r, 4i - r + 4)
+  const uint32_t r = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 15);
+  const uint4* sv = reinterpret_cast<const uint4*>(s - r);   // aligned vectors; vector i covers source bytes [16 i - r, 16 i - r + 16)
   uint4* dv = reinterpret_cast<uint4*>(d);
   if (r == 0) {
-    for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const uint32_t* p = sw + i * 4;
-      dv[i] = make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
-    }
+#pragma unroll 2
+    for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) dv[i] = __ldg(sv + i);
   } else {
-    const uint32_t sh = r * 8;
-    for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const uint32_t* p = sw + i * 4;
-      const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
-      dv[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    const uint32_t bs = (r & 3) * 8;
+    switch (r >> 2) {                                          // CTA-uniform
+      case 0: splice_copy_vec<0>(dv, sv, nvec, bs); break;
+      case 1: splice_copy_vec<1>(dv, sv, nvec, bs); break;
+      case 2: splice_copy_vec<2>(dv, sv, nvec, bs); break;
+      default: splice_copy_vec<3>(dv, sv, nvec, bs); break;
     }
   }
   for (uint64_t x = (nvec << 4) + threadIdx.x; x < n; x += blockDim.x) d[x] = s[x];   // tail
@@ -174,6 +185,81 @@ __global__ void __launch_bounds__(256) splice_kernel(const uint8_t* src, uint64_
     cur = k_end[k] < t1 ? k_end[k] : t1;
     if (k_end[k] > t1) break;                               // the rest of the tile is inside this match
     k++;
+  }
+}
+
+
+// ---- incremental passes -----------------------------------------------------------------
+// After a pass has replaced the kept occurrences of one needle, the matches of the NEW text are
+//   (a) the old matches that do not touch a replaced span, moved by the sum of the length deltas to their left, and
+//   (b) matches that contain at least one byte of a replacement, or straddle the junction a deletion left behind;
+//       they lie within max_len - 1 bytes of an edit.
+// So instead of rescanning the whole text (`go p $ replace ...`, Replacer.hs:242) the sorted match list is carried from
+// pass to pass: (a) is a filter + shift over the list, (b) a walk of the byte automaton over one small window per edit.
+// Matches of needles at or above the threshold can never be used again (`pMatch < threshold`, :253) and are dropped.
+// CaseSensitive, no empty needle (spans are `lenBytes` long and non-empty); other replacers rescan.
+
+// Append `key` for the calling lanes (any subset of a warp): one atomic per warp.
+__device__ __forceinline__ void append_key(uint64_t* out, unsigned long long* counter, uint64_t cap, uint64_t key) {
+  const unsigned active = __activemask();
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(active) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(active));
+  base = __shfl_sync(active, base, leader);
+  const unsigned long long slot = base + __popc(active & ((1u << lane) - 1u));
+  if (slot < cap) out[slot] = key;
+}
+
+// (a): keep the matches of still-eligible needles that touch no replaced span [k_start, k_end), shifted.
+__global__ void carry_matches_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, const uint32_t* len_of_rank,
+                                     uint32_t pass_id, const uint64_t* k_start, const uint64_t* k_end, const long long* k_shift, uint64_t K,
+                                     long long total_shift, uint64_t* out, unsigned long long* counter, uint64_t cap) {
+  const uint64_t mask = (1ull << rank_bits) - 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    const uint32_t rank = (uint32_t)(key & mask);
+    if (__ldg(id_of_rank + rank) <= pass_id) continue;        // at or above the new threshold
+    const uint64_t e = key >> rank_bits, s = e - __ldg(len_of_rank + rank);
+    uint64_t lo = 0, hi = K;                                  // first edit that ends after the match starts
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (k_end[mid] > s) hi = mid; else lo = mid + 1; }
+    if (lo < K && k_start[lo] < e) continue;                  // touches a replaced span
+    const long long shift = lo < K ? k_shift[lo] : total_shift;
+    append_key(out, counter, cap, ((uint64_t)((long long)e + shift) << rank_bits) | rank);
+  }
+}
+
+// (b): one thread per edit walks [new_start - (L - 1), new_start + repl_len + (L - 1)) of the NEW text from the root
+// state and reports the matches that touch its edit; a match that touches several edits is reported by the last one.
+__global__ void rescan_edits_kernel(DevAutomaton A, const uint8_t* text, uint64_t text_len, const uint64_t* k_start, const long long* k_shift, uint64_t K,
+                                    uint32_t repl_len, uint32_t pass_id, uint64_t* out, unsigned long long* counter, uint64_t cap) {
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < K; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ns = (uint64_t)((long long)k_start[j] + k_shift[j]);          // the replacement occupies [ns, ns + repl_len)
+    const bool has_next = j + 1 < K;
+    const uint64_t ns2 = has_next ? (uint64_t)((long long)k_start[j + 1] + k_shift[j + 1]) : 0;
+    const uint64_t halo = A.max_len - 1;
+    uint64_t p = ns > halo ? ns - halo : 0;
+    uint64_t end = ns + repl_len + halo; if (end > text_len) end = text_len;
+    uint32_t state = 0;
+    for (; p < end; p++) {
+      const uint32_t t = ac_step(A, state, __ldg(text + p));
+      state = t & ID_MASK;
+      if (!(t & OUT_FLAG)) continue;
+      const uint64_t e = p + 1;
+      for (uint32_t c = __ldg(A.first_out + state); c != NONE; c = __ldg(A.next_out + c)) {
+        const uint32_t olo = __ldg(A.own_off + c), ohi = __ldg(A.own_off + c + 1);
+        for (uint32_t o = olo; o < ohi; o++) {
+          const uint32_t rank = __ldg(A.own_rank + o);
+          if (__ldg(A.id_of_rank + rank) <= pass_id) continue;
+          const uint64_t s = e - __ldg(A.len_of_rank + rank);
+          // touches edit j: holds a replacement byte, or (deletion) spans the junction
+          const bool mine = repl_len ? (s < ns + repl_len && e > ns) : (s < ns && e > ns);
+          if (!mine) continue;
+          if (has_next && (repl_len ? (s < ns2 + repl_len && e > ns2) : (s < ns2 && e > ns2))) continue;   // the next edit reports it
+          append_key(out, counter, cap, (e << A.rank_bits) | rank);
+        }
+      }
+    }
   }
 }
 
@@ -257,11 +343,21 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
   Scalars* d_s = scal.as<Scalars>();
   Scalars h_s;
 
+  // carry the match list from pass to pass instead of rescanning (see carry_matches_kernel); AM_REPLACER_RESCAN=1 keeps
+  // the reference's literal pass structure (a full scan per pass) for A/B runs
+  const char* env_rescan = std::getenv("AM_REPLACER_RESCAN");   // read per call so that tests can A/B both forms
+  const bool force_rescan = env_rescan && std::atoi(env_rescan) != 0;
+  const bool incremental = r->cs == AM_CASE_SENSITIVE && !r->has_empty && !force_rescan;
+  bool have_list = false;
+  uint64_t n = 0;
+  g_last_rescans = 0;
   for (;;) {
-    // ---- 1. scan the current text --------------------------------------------------------------------
-    am_dev_text t{cur->p, len, 0, 0};
-    uint64_t n = 0;
-    if ((rc = find_all_sorted(a, ws, t, st, &n))) return done(rc);
+    // ---- 1. the matches of the current text: a full scan, or the list carried over from the previous pass ---------
+    if (!have_list) {
+      am_dev_text t{cur->p, len, 0, 0};
+      if ((rc = find_all_sorted(a, ws, t, st, &n))) return done(rc);
+      g_last_rescans++;
+    }
     g_last_passes++;
     if (n == 0) break;                             // (_, []) -> Just haystack (:230)
     // ---- 2. the best priority below the threshold ------------------------------------------------------
@@ -349,9 +445,42 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
       if ((e = cudaGetLastError()) != cudaSuccess) return done(cuda_fail(e, "splice launch"));
     }
     std::swap(cur, nxt);
+    const uint64_t old_len = len;
     len = new_len;
     if ((long long)id == last_id) break;           // p == minPriority: no needle is left (:241)
     prev_id = id;                                   // go p (:242)
+    // ---- 7. the next pass's matches without a rescan ----------------------------------------------------------
+    have_list = false;
+    if (incremental) {
+      (void)old_len;
+      const uint64_t cap = ws->keys_a_bytes / 8;
+      unsigned long long* d_n = reinterpret_cast<unsigned long long*>(ws->d_scalars);
+      cudaMemsetAsync(d_n, 0, 8, st);
+      {
+        unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+        g_kernel_launches++;
+        carry_matches_kernel<<<blocks, 256, 0, st>>>(ws->keys_b, n, rank_bits, a->dev.id_of_rank, a->dev.len_of_rank, id, kstart.as<uint64_t>(), kend.as<uint64_t>(),
+                                                    kshift.as<long long>(), K, total_shift, ws->keys_a, d_n, cap);
+      }
+      if (K) {
+        unsigned blocks = (unsigned)std::min<uint64_t>((K + 63) / 64, 148 * 16);
+        g_kernel_launches++;
+        rescan_edits_kernel<<<blocks, 64, 0, st>>>(a->dev, cur->as<uint8_t>(), len, kstart.as<uint64_t>(), kshift.as<long long>(), K, rl, id, ws->keys_a, d_n, cap);
+      }
+      unsigned long long n_new = 0;
+      cudaMemcpyAsync(&n_new, d_n, 8, cudaMemcpyDeviceToHost, st);
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "carry matches"));
+      if (n_new <= cap) {                          // (more than the key buffers hold: fall back to a rescan, which resizes them)
+        n = n_new;
+        if (n) {
+          const int end_bit = std::min(64, bitlen(len) + (int)rank_bits);
+          size_t stb = sort_temp_bytes(n, end_bit);
+          if ((rc = ws->need_sort_temp(stb))) return done(rc);
+          if ((e = sort_keys(ws->sort_temp, stb, ws->keys_a, ws->keys_b, n, end_bit, st)) != cudaSuccess) return done(cuda_fail(e, "radix sort"));
+        }
+        have_list = true;
+      }
+    }
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return done(cuda_fail(e, "replacer"));

@@ -149,6 +149,9 @@ int am_replacer_run(const am_replacer *r, am_u8slice hay, uint64_t max_len, uint
                     uint64_t *out_len, int *exceeded);
 /* Number of scan passes the last am_replacer_run on this thread performed. */
 uint64_t am_replacer_last_passes(void);
+/* Number of those passes that scanned the whole text: 1 when the match list could be carried from pass to pass
+ * (CaseSensitive, no empty needle: only the neighbourhood of each replacement is rescanned), else every pass. */
+uint64_t am_replacer_last_rescans(void);
 void am_free(void *p);
 
 /* ---- L1 text substrate used by the wrappers (Utf8.hs) ------------------------------------------

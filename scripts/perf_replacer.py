@@ -12,4 +12,4 @@ t0 = time.time(); hay = synth.fill_host(0, n, 63); synth.plant_host(hay, 0, 64, 
 r = replacer.build(0, list(zip(needles, repls)))
 for _ in range(2):
     t0 = time.time(); out = replacer.run(r, hay); dt = time.time() - t0
-    print("Replacer.run %d B -> %d B, %d passes, %.3f s (%.2f ms/pass, %.1f GB/s of scanned+written bytes)" % (n, len(out), r.last_passes, dt, dt / r.last_passes * 1e3, r.last_passes * 3.0 * n / dt / 1e9), flush=True)
+    print("Replacer.run %d B -> %d B, %d passes (%d full scans), %.3f s (%.2f ms/pass)" % (n, len(out), r.last_passes, r.last_rescans, dt, dt / r.last_passes * 1e3), flush=True)

@@ -430,3 +430,38 @@ def test_ac_bench_protocol(am, golden, tmp_path, capsys):
     cap = capsys.readouterr()
     assert cap.err.strip() == str(v["expected_count"])
     assert len([x for x in cap.out.strip().split("\t") if x]) == 5
+
+
+def test_stride2_cells_and_tail_compare(am, oracle, torch_cuda):
+    """q = 4 filter: one bitmap word answers two start positions (even p: cell A, odd p + 1: cell B) and survivors on
+    a single needle path are checked by a tail comparison.  Dense small-alphabet text so that needles start at every
+    residue of the 16-byte granule, the 1 KiB pair, the 4 KiB warp chunk and the 128 KiB CTA tile; needle sets with
+    shared prefixes (not a single path), duplicates (several ranks at one leaf), a needle of exactly q bytes, bytes
+    that share their low 5 bits (cells collide, only false positives), multi-byte UTF-8; unaligned device pointers."""
+    torch = torch_cuda
+    rng = np.random.default_rng(4242)
+    sets = [
+        ["abca", "bcab", "cabc", "abcab", "abcabc", "bca" + "abc" * 4, "abca"],          # prefixes of each other, duplicate
+        ["aaaa", "aaaab", "baaaa", "abab", "ababab", "bbbbbbbbbbbbbbbb"],                  # self-overlapping
+        ["aAb!", "!bAa", "Aa!b1", "a!A!a!A", "ABAB", "abab"],                             # 'a' 'A' '!' share their low 5 bits
+        ["åbcå", "💩ab", "ab💩", "ßßab", "abßß", "ẞẞ"],                                   # multi-byte code points
+    ]
+    alphabets = ["abc", "ab", "aA!b1B", "abåß💩ẞ"]
+    for needles, alpha in zip(sets, alphabets):
+        n_cp = (300 << 10) + int(rng.integers(0, 64))
+        idx = rng.integers(0, len(alpha), size=n_cp)
+        hb = "".join(alpha[int(i)] for i in idx[:n_cp]).encode("utf-8")
+        want = oracle.Machine(needles).find_all(np.frombuffer(hb, dtype=np.uint8), cap=len(hb) * 4)
+        m = machine(am, needles, force_kernel=2)
+        assert m.info()["kernel_kind"] == 2
+        for shift in (0, 1, 7, 15):
+            dev = torch.empty(len(hb) + 64, dtype=torch.uint8, device="cuda")
+            dev[shift:shift + len(hb)] = torch.frombuffer(bytearray(hb), dtype=torch.uint8).cuda()
+            ptr = dev.data_ptr() + shift
+            n = m.count_matches_dev(ptr, len(hb))
+            assert n == len(want), (needles, shift)
+            out = torch.empty(2 * (n + 16), dtype=torch.int64, device="cuda")
+            got_n = m.find_all_dev(ptr, len(hb), out.data_ptr(), n + 16)
+            assert got_n == n
+            got = out.cpu().numpy()[: 2 * n].view(am.automaton.MATCH_DTYPE)
+            assert np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (needles, shift)

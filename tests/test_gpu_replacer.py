@@ -103,3 +103,46 @@ def test_config4_idempotence_at_scale(am):
     again = am.replacer.run(r, out)
     assert again == out and r.last_passes == 1
     assert am.replacer.run_with_limit(r, len(out) - 1, hay) is None and am.replacer.run_with_limit(r, len(out) + (1 << 20), hay) == out
+
+
+def test_incremental_passes_equal_full_rescans(am, oracle, monkeypatch):
+    """the match list is carried from pass to pass (old matches that touch no edit are
+    shifted, only the neighbourhood of each replacement is rescanned).  Same bytes and pass count as the literal
+    form (AM_REPLACER_RESCAN=1: a full scan per pass) and as the oracle, on inputs built to stress the carry:
+    replacements that create lower-priority needles, deletions (matches across the junction), adjacent and
+    overlapping occurrences, replacements longer and shorter than the needle, needles that are substrings of others."""
+    R = am.replacer
+    rng = np.random.default_rng(77)
+    cases = [
+        ([("ab", ""), ("ba", "x"), ("aa", "b"), ("xb", "ab")], "ab" * 3000 + "a" + "ba" * 100),
+        ([("abc", "c"), ("cc", "abab"), ("ab", "ba"), ("bab", ""), ("aa", "c")], "abc" * 500 + "cab" * 500 + "aabbcc" * 300),
+        ([("aaa", "a"), ("aa", "bb"), ("bbb", "ab"), ("ab", "")], "a" * 4097 + "b" * 100 + "ab" * 777),
+        ([("tshirt", "banana"), ("shirt", "pear"), ("banana", "tshirts"), ("pear", "shirt"), ("anas", "")], "sweatshirts and shirttshirts " * 400),
+    ]
+    for _ in range(6):   # random cascades over a small alphabet: replacements are themselves made of needle fragments
+        frags = ["".join("abc"[int(i)] for i in rng.integers(0, 3, size=int(rng.integers(1, 4)))) for _ in range(6)]
+        pairs = []
+        for _ in range(int(rng.integers(3, 9))):
+            nd = "".join(frags[int(i)] for i in rng.integers(0, 6, size=int(rng.integers(1, 3))))
+            rp = "".join(frags[int(i)] for i in rng.integers(0, 6, size=int(rng.integers(0, 3))))
+            pairs.append((nd, rp))
+        hay = "".join(frags[int(i)] for i in rng.integers(0, 6, size=3000))
+        cases.append((pairs, hay))
+    for pairs, hay in cases:
+        o = oracle.Replacer(pairs)
+        want = o.run(hay)
+        r = R.build(0, pairs)
+        monkeypatch.delenv("AM_REPLACER_RESCAN", raising=False)
+        got = R.run(r, hay)
+        assert got == want, pairs
+        assert r.last_passes == o.passes and r.last_rescans == 1
+        monkeypatch.setenv("AM_REPLACER_RESCAN", "1")
+        assert R.run(r, hay) == want
+        assert r.last_passes == o.passes and r.last_rescans == o.passes
+    monkeypatch.delenv("AM_REPLACER_RESCAN", raising=False)
+    # run_with_limit sees the same `replacementLength` in both forms
+    pairs, hay = cases[1]
+    full = oracle.Replacer(pairs).run(hay)
+    r = R.build(0, pairs)
+    assert R.run_with_limit(r, len(full) + 4096, hay) == oracle.Replacer(pairs).run_with_limit(hay, len(full) + 4096)
+    assert R.run_with_limit(r, 10, hay) is None and oracle.Replacer(pairs).run_with_limit(hay, 10) is None
