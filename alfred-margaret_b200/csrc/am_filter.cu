@@ -37,7 +37,7 @@ constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
 constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
 constexpr int FK_SQ = 64;                        // survivor queue entries per warp
 constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
-constexpr uint64_t FK_SPAN = 1ull << 31;         // bytes per launch (survivors carry 32-bit offsets)
+constexpr uint64_t FK_SPAN = 1ull << 40;         // bytes per launch (one launch per scan in practice; survivors carry 64-bit offsets)
 // Build-time variants (A/B-tested on the GPU; the rejected ones -- warp-scan compaction of the candidates, bulk L2
 // prefetch, IMAD.HI row addressing, an out-of-line survivor drain -- are recorded in profiles/README.md):
 //   FK_DEBUG      compile the stage-isolation switches (AM_DEBUG_FLAGS=1: probes only, 2: no survivor walk)
@@ -49,7 +49,8 @@ struct FilterSmem {
   uint32_t filter[FILTER_WORDS];                 // 128 KiB: [row][bank]
   uint32_t t2[T2_WORDS];                         // 32 KiB
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
-  uint2 sq[FK_WARPS][FK_SQ];                     // 16 KiB: (offset from v_begin, q-gram)
+  unsigned long long sq_pos[FK_WARPS][FK_SQ];    // 16 KiB: survivor queue, offset from v_begin ...
+  uint32_t sq_g[FK_WARPS][FK_SQ];                //  8 KiB: ... and its q-gram
   unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
   uint32_t sq_n[FK_WARPS];
   uint32_t wkeys_n[FK_WARPS];
@@ -93,7 +94,7 @@ __device__ __forceinline__ void fk_flush(const ScanArgs& a, FilterSmem* sm, uint
 // start position is tried (failure-less, position-parallel formulation of Aho-Corasick).
 template <int MODE>
 __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
-                                               uint32_t v_rel, uint32_t g, unsigned long long& local_count) {
+                                               uint64_t v_rel, uint32_t g, unsigned long long& local_count) {
   const uint64_t v = c.v_begin + v_rel;
   if (v < c.a0) return;
   const uint64_t i = v - c.a0;
@@ -167,8 +168,7 @@ template <int MODE>
 __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
                                            unsigned long long& local_count, uint32_t n) {
   for (uint32_t k = c.lane; k < n; k += 32) {
-    const uint2 e = sm->sq[c.warp][k];
-    fk_deep_verify<MODE>(A, a, sm, c, e.x, e.y, local_count);
+    fk_deep_verify<MODE>(A, a, sm, c, sm->sq_pos[c.warp][k], sm->sq_g[c.warp][k], local_count);
   }
   __syncwarp();
   if (c.lane == 0) sm->sq_n[c.warp] = 0;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       tail = __ldg(reinterpret_cast<const uint32_t*>(base16 + gt));
     }
   };
-  auto process_pair = [&](const uint4& qa, const uint4& qb, uint32_t tail, uint32_t pair_rel) {
+  auto process_pair = [&](const uint4& qa, const uint4& qb, uint32_t tail, uint64_t tile_rel, uint32_t pair_rel) {
     // mirror the pair into the window (exact q-gram recovery for the few candidates)
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane), "r"(qa.x), "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane + 512u), "r"(qb.x), "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
@@ -385,9 +385,9 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
 #if FK_DEBUG
         if (a.debug & 2u) { local_count++; continue; }
 #endif
-        const uint32_t rel = pair_rel + o + (lane << 4);
+        const uint64_t rel = tile_rel + (pair_rel + o + (lane << 4));
         const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-        if (qi < FK_SQ) sm->sq[warp][qi] = make_uint2(rel, g);
+        if (qi < FK_SQ) { sm->sq_pos[warp][qi] = rel; sm->sq_g[warp][qi] = g; }
         else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
       }
     }
@@ -402,15 +402,16 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   if (blockIdx.x < num_tiles) load_pair(g_next, cA, cB, tC);
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
-    const uint32_t chunk_rel = (uint32_t)(tile * FK_TILE) + warp * FK_CHUNK;   // this warp's chunk, relative to v_begin
+    const uint64_t tile_rel = tile * FK_TILE;              // this tile, relative to v_begin
+    const uint32_t chunk_rel = warp * FK_CHUNK;            // this warp's chunk, relative to the tile
 #pragma unroll 1
     for (int pair = 0; pair < FK_PAIRS; pair += 2) {
       g_next += 64;                                        // odd pair of the same chunk
       load_pair(g_next, nA, nB, tN);
-      process_pair(cA, cB, tC, chunk_rel + (uint32_t)pair * 1024u);
+      process_pair(cA, cB, tC, tile_rel, chunk_rel + (uint32_t)pair * 1024u);
       g_next += pair + 2 < FK_PAIRS ? 64 : tile_stride_granules - (FK_PAIRS - 1) * 64;   // next even pair: same chunk, or this warp's chunk in the CTA's next tile
       load_pair(g_next, cA, cB, tC);                       // beyond the CTA's last tile this is a clamped, unused load
-      process_pair(nA, nB, tN, chunk_rel + (uint32_t)pair * 1024u + 1024u);
+      process_pair(nA, nB, tN, tile_rel, chunk_rel + (uint32_t)pair * 1024u + 1024u);
     }
   }
   fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
