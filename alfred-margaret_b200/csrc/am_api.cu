@@ -263,7 +263,7 @@ int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_low
   // thousand distinct q-grams its false-positive rate (keys / 65 536) swamps the second level, and the
   // per-segment walk is the better kernel.  force_kernel = 2 overrides the heuristic.
   const bool filter_ok = H.q > 0;   // IgnoreCase runs the filter on a lowered copy of the text (launch_scan)
-  const bool filter_good = filter_ok && H.filter_keys <= 16384;   // measured: 10 k needles 715 GB/s (filter) vs 445 GB/s (walk)
+  const bool filter_good = filter_ok && H.filter_keys <= 65536;   // measured (r1d): 20 k needles 1043 GB/s (filter) vs 309 (walk), 40 k 559 vs 234, 100 k 142 vs 212
   a->kernel_kind = (force == 2 && filter_ok) || (force != 1 && filter_good) ? 2 : 1;
   if (force == 2 && a->kernel_kind != 2) { delete a; return fail(AM_E_UNSUPPORTED, "filter kernel not applicable to this needle set"); }
   if (want_dev == -2) { a->device = -1; *out = a; return AM_OK; }  // host image only (tests / introspection)

@@ -126,7 +126,10 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   terms.reserve(n);
   std::vector<uint32_t> len_bytes(n), len_cps(n);
   A->min_len = 0xFFFFFFFFu; A->max_len = 0; A->max_len_cps = 0; A->num_empty = 0;
-  constexpr uint64_t MAX_VARIANTS = 64;
+  // variants per needle and states overall before the automaton gives up on the lowered-copy scheme (a 16-letter needle
+  // with 12 letters that have a length-changing pre-image has 4 096 variants; realistic sets stay far below both)
+  constexpr uint64_t MAX_VARIANTS = 4096;
+  constexpr size_t MAX_VARIANT_STATES = 8u << 20;
   auto insert = [&](const uint8_t* d, uint32_t len, uint32_t id) {
     uint32_t s = 0;
     for (uint32_t k = 0; k < len; k++) s = B.add(s, d[k]);
@@ -153,7 +156,7 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     uint64_t combos = 1;
     for (uint32_t c : ncp) { auto it = preimages.find(c); if (it != preimages.end()) combos *= 1 + it->second.size(); if (combos > MAX_VARIANTS) break; }
     if (combos == 1) continue;
-    if (combos > MAX_VARIANTS) { A->ic_copy_exact = false; continue; }   // too many variants: this automaton uses the sentinel + fallback scheme
+    if (combos > MAX_VARIANTS || B.parent.size() > MAX_VARIANT_STATES) { A->ic_copy_exact = false; continue; }   // too many variants: this automaton uses the sentinel + fallback scheme
     std::vector<uint32_t> choice(ncp.size(), 0);
     for (uint64_t v = 1; v < combos; v++) {                // odometer over the pre-image choices (0 = the lowered code point itself)
       for (size_t p = 0; p < ncp.size(); p++) {
@@ -434,7 +437,16 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       }
     } else {
       A->filter2.assign(T2_WORDS, 0);
-      for (auto& kv : keys) { uint32_t b2 = filter2_bit(kv.first); A->filter2[b2 >> 5] |= 1u << (b2 & 31); }
+      auto set_bit = [&](uint32_t word0, uint32_t bit) { A->filter2[word0 + (bit >> 5)] |= 1u << (bit & 31); };
+      for (auto& kv : keys) {
+        if (q != 4) { set_bit(0, filter2_bit(kv.first)); continue; }
+        const uint32_t g = kv.first, s = kv.second;        // q = 4: closed 4-grams + the 5-grams of the needles that go on
+        if (A->own_off[s + 1] > A->own_off[s]) set_bit(T2A_WORD0, t2a_bit(g));
+        for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) {
+          set_bit(T2B_WORD0, t2b_bit(g, A->child_byte[c]));
+          set_bit(T2C_WORD0, t2c_bit(g, A->child_byte[c]));
+        }
+      }
     }
   }
   return AM_OK;

@@ -283,6 +283,14 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
     if (Q4) nb = (hi >> sh) & 0xFFu;
     else nb = (uint32_t)((((unsigned long long)hi << 32) | lo) >> (sh + 8u * A.q)) & 0xFFu;
     return nb == (aux & 0xFFu);
+  } else if (Q4) {
+    // needle set too large for the exact table: closed 4-grams (T2A) or a fifth byte that continues a needle (T2B, T2C)
+    const uint32_t nb = (hi >> sh) & 0xFFu;                 // text byte right after the 4-gram
+    const uint32_t ba = t2a_bit(g), bb = t2b_bit(g, nb), bc = t2c_bit(g, nb);
+    const uint32_t wa = lds32(t2_s + ((T2A_WORD0 + (ba >> 5)) << 2));
+    const uint32_t wb = lds32(t2_s + ((T2B_WORD0 + (bb >> 5)) << 2));
+    const uint32_t wc = lds32(t2_s + ((T2C_WORD0 + (bc >> 5)) << 2));
+    return ((wa >> (ba & 31)) | ((wb >> (bb & 31)) & (wc >> (bc & 31)))) & 1u;
   } else {
     const uint32_t b2 = (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS);
     return (lds32(t2_s + ((b2 >> 5) << 2)) >> (b2 & 31)) & 1u;

@@ -112,6 +112,11 @@ struct HostAutomaton {
 int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower,
                          HostAutomaton* out, std::string* err);
 
+#if defined(__CUDACC__)
+#define AM_HD_DECL __host__ __device__ __forceinline__
+#else
+#define AM_HD_DECL inline
+#endif
 inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
 // Build-time variants of the filter kernel (A/B-tested on the GPU):
 //   FK_S2         stride-2 probe for q = 4: ONE bitmap word answers "does a needle start at p" and "does a needle
@@ -170,6 +175,18 @@ inline void filter_cells_s2(uint32_t g, uint32_t* row_a, uint32_t* bit_a, uint32
   *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
+// Second level for q = 4 needle sets too large for the exact table (T2_MAX_EXACT_KEYS): three bitmaps in the 32 KiB.
+//   T2A (64 Ki bits):  4-grams that END a needle (a needle of exactly four bytes);
+//   T2B (128 Ki bits) and T2C (64 Ki bits, independent hash): the 5-grams of the needles that go on -- a candidate whose
+//   4-gram is a needle prefix survives only if its fifth byte continues some needle as well.
+// A candidate survives if T2A[g4] or (T2B[g5] and T2C[g5]).  Must match fk_phase_a.
+constexpr int T2A_LOG2 = 16, T2B_LOG2 = 17, T2C_LOG2 = 16;
+constexpr uint32_t T2A_WORD0 = 0, T2B_WORD0 = (1u << T2A_LOG2) / 32, T2C_WORD0 = T2B_WORD0 + (1u << T2B_LOG2) / 32;
+static_assert(T2C_WORD0 + (1u << T2C_LOG2) / 32 == (uint32_t)T2_WORDS, "T2 bitmap geometry");
+constexpr uint32_t HASH_MUL3 = 0xC2B2AE35u;
+AM_HD_DECL uint32_t t2a_bit(uint32_t g4) { return (g4 * HASH_MUL2) >> (32 - T2A_LOG2); }
+AM_HD_DECL uint32_t t2b_bit(uint32_t g4, uint32_t b4) { return ((g4 * HASH_MUL2) ^ (b4 * HASH_MUL)) >> (32 - T2B_LOG2); }
+AM_HD_DECL uint32_t t2c_bit(uint32_t g4, uint32_t b4) { return ((g4 ^ (b4 * 0x01000193u)) * HASH_MUL3) >> (32 - T2C_LOG2); }
 inline uint32_t t2_bucket(uint32_t g) { return (g * HASH_MUL2) >> (32 - T2_LOG2_BUCKETS); }
 // Table hashes (host + device); callers mask with the table's power-of-two mask.
 #if defined(__CUDACC__)

@@ -302,6 +302,12 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, S
 //    it is left unchanged in the copy, where the variant needles match it -- exact, no second pass;
 //  * keep = 0: it is overwritten with 0xFF bytes (never part of a valid UTF-8 needle) and counted; the host
 //    then falls back to the exact per-code-point walk kernel for that text.
+// SWAR toLowerAscii (Utf8.hs:131-135) on the ASCII bytes of a word; bytes >= 0x80 pass through.
+__device__ __forceinline__ uint32_t lower_ascii_word(uint32_t q) {
+  const uint32_t q7 = q & 0x7f7f7f7fu;                       // bit 7 of (c + 0x3f) & ~(c + 0x25) marks 'A'..'Z'
+  return q | ((((q7 + 0x3f3f3f3fu) & ~(q7 + 0x25252525u)) & ~q & 0x80808080u) >> 2);
+}
+
 __global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_t* text, uint64_t text_len, uint8_t* out /* same misalignment as text */,
                                                     unsigned int* exceptions, int keep) {
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(text);
@@ -310,65 +316,58 @@ __global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_
   uint4* out16 = reinterpret_cast<uint4*>(out - a0);
   const uint32_t* in32 = reinterpret_cast<const uint32_t*>(in16);
   const uint64_t nvec = (a0 + text_len + 15) >> 4;
+  const uint64_t lo = a0, hi = a0 + text_len;                 // virtual byte range of the text
   for (uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < nvec; gi += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 q = ld_stream_v4(in16 + gi);
-    if (((q.x | q.y | q.z | q.w) & 0x80808080u) == 0) {
-      // toLowerAscii (Utf8.hs:131-135) on 16 bytes at once: bit 7 of (c + 0x3f) & ~(c + 0x25) marks 'A'..'Z'
-      uint4 r;
-      r.x = q.x | ((((q.x + 0x3f3f3f3fu) & ~(q.x + 0x25252525u)) & 0x80808080u) >> 2);
-      r.y = q.y | ((((q.y + 0x3f3f3f3fu) & ~(q.y + 0x25252525u)) & 0x80808080u) >> 2);
-      r.z = q.z | ((((q.z + 0x3f3f3f3fu) & ~(q.z + 0x25252525u)) & 0x80808080u) >> 2);
-      r.w = q.w | ((((q.w + 0x3f3f3f3fu) & ~(q.w + 0x25252525u)) & 0x80808080u) >> 2);
-      out16[gi] = r;
-      continue;
-    }
-    // general path: bytes [-4, 20) of the granule in a local window, every code point that overlaps [0, 16)
-    // is decoded (decodeN, Utf8.hs:344-350), lowered, re-encoded (unicode2utf8, :154-160)
-    uint8_t win[24], res[16];
-    const uint32_t prev = gi > 0 ? __ldg(in32 + gi * 4 - 1) : 0u;
-    const uint32_t next = gi + 1 < nvec ? __ldg(in32 + (gi + 1) * 4) : 0u;
-    const uint32_t wds[6] = {prev, q.x, q.y, q.z, q.w, next};
+    // ASCII letters of all four words at once; an all-ASCII granule is done (no code point reaches into it)
+    uint32_t R[6] = {0u, lower_ascii_word(q.x), lower_ascii_word(q.y), lower_ascii_word(q.z), lower_ascii_word(q.w), 0u};
+    if (((q.x | q.y | q.z | q.w) & 0x80808080u) != 0) {
+      // Window of bytes [-4, 20) of the granule as six words.  Every code point above ASCII whose lead byte lies in
+      // window bytes [1, 20) and that overlaps the granule is decoded (decodeN, Utf8.hs:344-350), lowered, re-encoded
+      // (unicode2utf8, :154-160).  The word index is static (unrolled), so the bytes of a code point come out of a word
+      // pair by a funnel shift and go back in by a 64-bit mask -- no byte arrays, no local memory.
+      const uint32_t prev = gi > 0 ? __ldg(in32 + gi * 4 - 1) : 0u;
+      const uint32_t next = gi + 1 < nvec ? __ldg(in32 + (gi + 1) * 4) : 0u;
+      const uint32_t W[6] = {prev, q.x, q.y, q.z, q.w, next};
+      const uint64_t vbase = (gi << 4) - 4;                   // virtual index of window byte 0 (wraps for gi = 0; only used with j >= 4 there)
 #pragma unroll
-    for (int i = 0; i < 24; i++) win[i] = (uint8_t)(wds[i >> 2] >> (8 * (i & 3)));
-#pragma unroll
-    for (int i = 0; i < 16; i++) res[i] = win[4 + i];
-    const long long vbase = (long long)(gi << 4) - 4;        // virtual index of win[0]
-    const long long lo = (long long)a0, hi = (long long)(a0 + text_len);
-    for (int p = 1; p < 20; p++) {                            // p = index in win of a potential lead byte
-      const long long v = vbase + p;
-      if (v < lo || v >= hi) continue;
-      const uint32_t b0 = win[p];
-      if ((b0 & 0xC0u) == 0x80u) continue;                    // continuation byte: handled with its lead
-      uint32_t len, cp;
-      if (b0 < 0x80u) { len = 1; cp = b0; }
-      else if (b0 < 0xE0u) { len = 2; cp = b0 & 0x1Fu; }
-      else if (b0 < 0xF0u) { len = 3; cp = b0 & 0x0Fu; }
-      else { len = 4; cp = b0 & 0x07u; }
-      if (p + (int)len <= 4) continue;                        // ends before the granule
-      if (p >= 20) break;
-      bool whole = v + len <= hi && p + (int)len <= 24;       // truncated at the text end / window: copy through
-      for (uint32_t k = 1; k < len && whole; k++) cp = (cp << 6) | (win[p + k] & 0x3Fu);
-      if (!whole) continue;
-      const uint32_t l = lower_cp(A, cp);
-      uint8_t enc[4]; uint32_t elen;
-      if (l < 0x80u) { enc[0] = (uint8_t)l; elen = 1; }
-      else if (l < 0x800u) { enc[0] = 0xC0u | (l >> 6); enc[1] = 0x80u | (l & 0x3Fu); elen = 2; }
-      else if (l < 0x10000u) { enc[0] = 0xE0u | (l >> 12); enc[1] = 0x80u | ((l >> 6) & 0x3Fu); enc[2] = 0x80u | (l & 0x3Fu); elen = 3; }
-      else { enc[0] = 0xF0u | (l >> 18); enc[1] = 0x80u | ((l >> 12) & 0x3Fu); enc[2] = 0x80u | ((l >> 6) & 0x3Fu); enc[3] = 0x80u | (l & 0x3Fu); elen = 4; }
-      const bool same = elen == len;
-      if (!same && keep) continue;                                // res already holds the original bytes
-      if (!same && p >= 4 && p < 20) atomicAdd(exceptions, 1u);   // counted once, by the granule that holds the lead byte
-      for (uint32_t k = 0; k < len; k++) {
-        const int qi = p + (int)k - 4;
-        if (qi >= 0 && qi < 16) res[qi] = same ? enc[k] : (uint8_t)0xFF;
+      for (int wi = 0; wi < 5; wi++) {
+        uint32_t mw = W[wi] & (W[wi] << 1) & 0x80808080u;    // bit 7 of every byte 11xxxxxx: a lead byte of a 2..4-byte code point
+        if (wi == 0) mw &= 0xFFFFFF00u;                       // window byte 0 cannot reach the granule
+        while (mw) {
+          const uint32_t k = (uint32_t)(__ffs((int)mw) - 1) >> 3;   // byte of the word
+          mw &= mw - 1;
+          const uint32_t g = __funnelshift_r(W[wi], W[wi + 1], 8 * k);   // the lead byte and the three that follow
+          const uint32_t b0 = g & 0xFFu;
+          uint32_t len, cp;
+          if (b0 < 0xE0u) { len = 2; cp = ((b0 & 0x1Fu) << 6) | ((g >> 8) & 0x3Fu); }
+          else if (b0 < 0xF0u) { len = 3; cp = ((b0 & 0x0Fu) << 12) | (((g >> 8) & 0x3Fu) << 6) | ((g >> 16) & 0x3Fu); }
+          else { len = 4; cp = ((b0 & 0x07u) << 18) | (((g >> 8) & 0x3Fu) << 12) | (((g >> 16) & 0x3Fu) << 6) | ((g >> 24) & 0x3Fu); }
+          const uint32_t j = 4u * wi + k;                     // window byte of the lead
+          if (j + len <= 4u) continue;                        // ends before the granule
+          const uint64_t v = vbase + j;
+          if ((gi == 0 && j < 4u) || v < lo || v + len > hi) continue;   // outside / truncated by the text: copied through
+          const uint32_t l = lower_cp(A, cp);
+          if (l == cp) continue;
+          uint32_t e, elen;
+          if (l < 0x80u) { e = l; elen = 1; }
+          else if (l < 0x800u) { e = (0xC0u | (l >> 6)) | ((0x80u | (l & 0x3Fu)) << 8); elen = 2; }
+          else if (l < 0x10000u) { e = (0xE0u | (l >> 12)) | ((0x80u | ((l >> 6) & 0x3Fu)) << 8) | ((0x80u | (l & 0x3Fu)) << 16); elen = 3; }
+          else { e = (0xF0u | (l >> 18)) | ((0x80u | ((l >> 12) & 0x3Fu)) << 8) | ((0x80u | ((l >> 6) & 0x3Fu)) << 16) | ((0x80u | (l & 0x3Fu)) << 24); elen = 4; }
+          if (elen != len) {
+            if (keep) continue;                               // stays as it is: the needle variants match it
+            if (*reinterpret_cast<volatile unsigned int*>(exceptions) == 0) *exceptions = 1u;   // only zero / non-zero matters
+            e = 0xFFFFFFFFu;                                  // marked: never part of a valid UTF-8 needle
+          }
+          const uint32_t m32 = 0xFFFFFFFFu >> (32u - 8u * len);                   // the code point's bytes, at byte k of word wi
+          e &= m32;
+          const uint32_t sh = 8u * k;
+          R[wi] = (R[wi] & ~(m32 << sh)) | (e << sh);
+          R[wi + 1] = (R[wi + 1] & ~__funnelshift_l(m32, 0u, sh)) | __funnelshift_l(e, 0u, sh);   // the part that spills into the next word
+        }
       }
     }
-    uint4 r;
-    r.x = res[0] | (res[1] << 8) | (res[2] << 16) | ((uint32_t)res[3] << 24);
-    r.y = res[4] | (res[5] << 8) | (res[6] << 16) | ((uint32_t)res[7] << 24);
-    r.z = res[8] | (res[9] << 8) | (res[10] << 16) | ((uint32_t)res[11] << 24);
-    r.w = res[12] | (res[13] << 8) | (res[14] << 16) | ((uint32_t)res[15] << 24);
-    out16[gi] = r;
+    out16[gi] = make_uint4(R[1], R[2], R[3], R[4]);
   }
 }
 

@@ -13,7 +13,8 @@ def timeit(f, reps=3):
     return min(ts)
 n = 1 << 30
 dev = torch.empty(n, dtype=torch.uint8, device="cuda")
-for label, nn, lo, hi, cs, kind in (("C2 walk", 1000, 4, 16, 0, 1), ("10k CS auto", 10000, 4, 16, 0, 0), ("10k CS filter-forced", 10000, 4, 16, 0, 2), ("100k CS auto", 100000, 6, 16, 0, 0),
+for label, nn, lo, hi, cs, kind in (("C2 walk", 1000, 4, 16, 0, 1), ("10k CS auto", 10000, 4, 16, 0, 0), ("10k CS filter-forced", 10000, 4, 16, 0, 2), ("20k CS filter-forced", 20000, 4, 16, 0, 2), ("20k CS walk", 20000, 4, 16, 0, 1), ("40k CS filter-forced", 40000, 4, 16, 0, 2), ("40k CS walk", 40000, 4, 16, 0, 1),
+                                    ("100k CS auto", 100000, 6, 16, 0, 0), ("100k CS filter-forced", 100000, 6, 16, 0, 2),
                                     ("1k IC auto", 1000, 4, 16, 1, 0), ("10k IC auto", 10000, 4, 16, 1, 0), ("10k IC walk", 10000, 4, 16, 1, 1)):
     needles = synth.random_needles(nn, 42, lo, hi)
     synth.fill_dev(dev.data_ptr(), n, 0, 43, alphabet=(synth.AZ + synth.AZ.upper() if cs else synth.AZ)); synth.plant_dev(dev.data_ptr(), n, 0, 44, needles)

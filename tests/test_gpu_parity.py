@@ -285,7 +285,8 @@ def test_ignore_case_length_changing_variants(am, oracle, lower_dense):
     sets = {
         "variants": base,
         "dead needles": base[:50] + ["K", "\u212a", "ak\u212b", "Åk", "ẞ", "İi", "kȺ"],    # never match
-        "fallback": base[:50] + ["kkkkkkk", "iiißßßkk"],                                  # > 64 variants each
+        "many variants": base[:50] + ["kkkkkkk", "iiißßßkk"],                             # 128 / 256 variants each
+        "fallback": base[:50] + ["k" * 13, "iiißßßkkiißßk"],                              # > 4 096 variants each
         "empty needle": base[:20] + [""],
     }
     for name, needles in sets.items():
@@ -378,9 +379,10 @@ def test_large_positions_and_kernel_choice(am, oracle, torch_cuda):
         rec = out[: 2 * k].cpu().numpy().view(am.automaton.MATCH_DTYPE)
         assert k == len(want) and np.array_equal(rec["end_pos"].astype(np.int64) - base, want["pos"]) and np.array_equal(rec["needle_id"].astype(np.int64), want["value"])
     assert machine(am, synth.random_needles(1000, 42)).info()["kernel_kind"] == 2
-    big = machine(am, synth.random_needles(40000, 43, 6, 12))
+    assert machine(am, synth.random_needles(40000, 43, 6, 12)).info()["kernel_kind"] == 2
+    big = machine(am, synth.random_needles(100000, 43, 6, 12))
     assert big.info()["kernel_kind"] == 1                      # too many distinct q-grams for the shared-memory bitmap
-    forced = machine(am, synth.random_needles(40000, 43, 6, 12), force_kernel=2)
+    forced = machine(am, synth.random_needles(100000, 43, 6, 12), force_kernel=2)
     hay = synth.fill_host(0, 1 << 20, 44)
     assert as_pairs(forced.find_all(hay)) == as_pairs(big.find_all(hay))
 
