@@ -127,7 +127,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
   sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
   static const uint32_t dbg = []() { const char* e = std::getenv("AM_DEBUG_FLAGS"); return e ? (uint32_t)std::atoi(e) : 0u; }();
-  sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q);
+  sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q, a->dev.t2_exact != 0);
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   const bool prof = g_profile.load(std::memory_order_relaxed) != 0;

@@ -367,10 +367,11 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     A->tails.clear();
     A->jump_mask = cap - 1;
     for (auto& kv : keys) {
-      const int copies = filter_copies(q);
+      const bool exact = keys.size() <= T2_MAX_EXACT_KEYS;
+      const int copies = filter_copies(q, exact);
       if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
         uint32_t ra, ba, rb, bb;
-        filter_cells_s2(kv.first, &ra, &ba, &rb, &bb);
+        filter_cells_s2(kv.first, filter_rowbits(copies), &ra, &ba, &rb, &bb);
         for (int c = 0; c < copies; c++) {
           A->filter[(size_t)ra * copies + c] |= 1u << ba;
           A->filter[(size_t)rb * copies + c] |= 1u << bb;

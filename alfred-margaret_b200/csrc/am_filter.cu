@@ -224,10 +224,12 @@ __device__ __forceinline__ uint32_t fk_probe16(uint32_t filt_lane, uint32_t qmas
 // HASH_MUL << 8, which discards its top byte -- and the two bits are picked by rotating the word by text[p] and by
 // text[p + 4] (SHF uses the low 5 bits of the register, so any register whose low byte is that text byte serves).
 // Per two text bytes: 1.5 + 1 + 2 + 2 ALU-pipe instructions, 2 IMAD, 1 LDS (stride-1: 7.5, 4, 2).
+template <int ROWBITS>
 __device__ __forceinline__ uint32_t fk_row_addr(uint32_t y, uint32_t krow, uint32_t filt_lane) {
-  return (y >> (32 - FILTER_ROWBITS_S2)) * krow + filt_lane;   // SHF + IMAD (krow is a run-time value: keeps the address an IMAD)
+  return (y >> (32 - ROWBITS)) * krow + filt_lane;   // SHF + IMAD (krow is a run-time value: keeps the address an IMAD)
 }
 
+template <int ROWBITS>
 __device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t krow, uint32_t m,
                                                   uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
   const uint32_t w[5] = {w0, w1, w2, w3, w4};
@@ -240,13 +242,13 @@ __device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t k
   for (int k = 3; k >= 0; k--) {
     {  // p = 4k + 2: positions 4k + 3 (cell B, private byte text[4k + 6]) and 4k + 2 (cell A, text[4k + 2])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 24) * HASH_MUL_S2;
-      const uint32_t word = lds32(fk_row_addr(y, krow, filt_lane));
+      const uint32_t word = lds32(fk_row_addr<ROWBITS>(y, krow, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, h[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, h[k]), m, 1);
     }
     {  // p = 4k: positions 4k + 1 (cell B, text[4k + 4]) and 4k (cell A, text[4k])
       const uint32_t y = __funnelshift_r(w[k], w[k + 1], 8) * HASH_MUL_S2;
-      const uint32_t word = lds32(fk_row_addr(y, krow, filt_lane));
+      const uint32_t word = lds32(fk_row_addr<ROWBITS>(y, krow, filt_lane));
       m = __funnelshift_l(__funnelshift_l(word, word, w[k + 1]), m, 1);
       m = __funnelshift_l(__funnelshift_l(word, word, w[k]), m, 1);
     }
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   const uint64_t nvec = (a0 + a.text_len + 15) >> 4;      // 16-byte granules overlapping the text (>= 1 here)
   uint32_t smem0;
   asm("mov.u32 %0, am_fk_smem;" : "=r"(smem0));
-  const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & ((Q4 && FK_S2 ? FK_COPIES_S2 : FK_COPIES_S1) - 1u)) << 2);
+  const uint32_t filt_lane = smem0 + (uint32_t)offsetof(FilterSmem, filter) + ((lane & ((Q4 && FK_S2 ? filter_copies_s2(T2X) : FK_COPIES_S1) - 1u)) << 2);
   const uint32_t win_s = smem0 + (uint32_t)offsetof(FilterSmem, window) + warp * (FK_WIN_WORDS * 4u);
   const uint32_t win_lane = win_s + (lane << 4);
   const uint32_t t2_s = smem0 + (uint32_t)offsetof(FilterSmem, t2);
@@ -372,8 +374,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
     const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail : qb.x, (lane + 1) & 31);
     uint32_t m = 0;                                        // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
     if (Q4 && FK_S2) {
-      m = fk_probe16_s2(filt_lane, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
-      m = fk_probe16_s2(filt_lane, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
+      m = fk_probe16_s2<filter_rowbits(filter_copies_s2(T2X))>(filt_lane, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
+      m = fk_probe16_s2<filter_rowbits(filter_copies_s2(T2X))>(filt_lane, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);
     } else {
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qb.x, qb.y, qb.z, qb.w, w4B);
       m = fk_probe16<Q4>(filt_lane, A.qmask, a.krow, m, qa.x, qa.y, qa.z, qa.w, w4A);

@@ -145,6 +145,9 @@ inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (
 #ifndef FK_COPIES_S2
 #define FK_COPIES_S2 2
 #endif
+#ifndef FK_COPIES_S2_BIG     // needle sets beyond the exact second level (> T2_MAX_EXACT_KEYS q-grams): ONE copy of 1 Mi bits
+#define FK_COPIES_S2_BIG 1   // (a few more bank conflicts per probe, half the false candidates -- they dominate there)
+#endif
 #ifndef FK_COPIES_S1
 #define FK_COPIES_S1 16
 #endif
@@ -152,10 +155,13 @@ inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (
 #define FK_WB 1
 #endif
 constexpr int filter_rowbits(int copies) { return copies == 32 ? 10 : copies == 16 ? 11 : copies == 8 ? 12 : copies == 4 ? 13 : copies == 2 ? 14 : 15; }
-constexpr int FILTER_ROWBITS_S2 = filter_rowbits(FK_COPIES_S2), FILTER_ROWBITS_S1 = filter_rowbits(FK_COPIES_S1);
-static_assert((1 << FILTER_ROWBITS_S2) * FK_COPIES_S2 == FILTER_WORDS && (1 << FILTER_ROWBITS_S1) * FK_COPIES_S1 == FILTER_WORDS, "filter geometry");
+constexpr int FILTER_ROWBITS_S1 = filter_rowbits(FK_COPIES_S1);
+static_assert((1 << filter_rowbits(FK_COPIES_S2)) * FK_COPIES_S2 == FILTER_WORDS && (1 << filter_rowbits(FK_COPIES_S2_BIG)) * FK_COPIES_S2_BIG == FILTER_WORDS &&
+              (1 << FILTER_ROWBITS_S1) * FK_COPIES_S1 == FILTER_WORDS, "filter geometry");
 inline bool filter_is_s2(uint32_t q) { return FK_S2 && q == 4; }
-inline int filter_copies(uint32_t q) { return filter_is_s2(q) ? FK_COPIES_S2 : FK_COPIES_S1; }
+// Copies of the bitmap for an automaton: `exact` = its q-grams fit the exact second-level table (t2_exact).
+constexpr int filter_copies_s2(bool exact) { return exact ? FK_COPIES_S2 : FK_COPIES_S2_BIG; }
+inline int filter_copies(uint32_t q, bool exact) { return filter_is_s2(q) ? filter_copies_s2(exact) : FK_COPIES_S1; }
 // Filter cell of a (masked) q-gram: row and bit 0..31.  Must match the device code.
 inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
   const uint32_t x = g * HASH_MUL;
@@ -168,10 +174,10 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
 //   cell A (needle starts at the even position p):      row of (n1, n2, n3), bit chosen by n0
 //   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
 constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
-inline void filter_cells_s2(uint32_t g, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
-  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - FILTER_ROWBITS_S2);
+inline void filter_cells_s2(uint32_t g, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
+  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - rowbits);
   *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31
-  *row_b = (g * HASH_MUL_S2) >> (32 - FILTER_ROWBITS_S2);
+  *row_b = (g * HASH_MUL_S2) >> (32 - rowbits);
   *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
 }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
