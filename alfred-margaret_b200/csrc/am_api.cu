@@ -59,7 +59,7 @@ static int upload(am_automaton* a, const std::vector<T>& v, const T** out) {
 }
 
 Workspace::~Workspace() {
-  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b})
+  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases})
     if (p) cudaFree(p);
   if (h_scalars) cudaFreeHost(h_scalars);
 }
@@ -86,6 +86,12 @@ int Workspace::need_aux(uint64_t a_bytes, uint64_t b_bytes) {
   int rc = ws_grow((void**)&aux_a, &aux_a_bytes, a_bytes, "aux");
   if (rc) return rc;
   return ws_grow((void**)&aux_b, &aux_b_bytes, b_bytes, "aux");
+}
+
+int Workspace::need_segs(uint64_t n) {
+  int rc = ws_grow((void**)&seg_counts, &seg_counts_bytes, n * 4 + 16, "segment counters");
+  if (rc) return rc;
+  return ws_grow((void**)&seg_bases, &seg_bases_bytes, n * 8 + 16, "segment bases");
 }
 
 Workspace* acquire_ws(const am_automaton* ca) {
@@ -130,6 +136,22 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q, a->dev.t2_exact != 0);
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  // EMIT on the filter kernel: keys go into per-segment slots of keys_a (first half) + an overflow area (second half)
+  ws->emit_segmented = false;
+  sa.seg_counts = nullptr; sa.seg_shift = SEG_SHIFT; sa.seg_cap = 0; sa.ovf_base = 0; sa.ovf_cap = 0;
+  if (mode == MODE_EMIT && a->kernel_kind == 2 && t.text_len > t.report_begin) {
+    const uint64_t num_segs = ((t.text_len - t.report_begin) + (1ull << SEG_SHIFT) - 1) >> SEG_SHIFT;
+    uint64_t per = (sa.cap / 2) / num_segs;
+    uint32_t seg_cap = 0;
+    if (per >= 16) { seg_cap = 16; while (seg_cap * 2 <= per && seg_cap < SEG_CAP_MAX) seg_cap *= 2; }
+    int rc = ws->need_segs(num_segs);
+    if (rc) return rc;
+    e = cudaMemsetAsync(ws->seg_counts, 0, (num_segs + 1) * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    ws->num_segs = num_segs; ws->seg_cap = seg_cap; ws->ovf_base = num_segs * seg_cap; ws->ovf_cap = sa.cap - ws->ovf_base;
+    sa.seg_counts = ws->seg_counts; sa.seg_cap = seg_cap; sa.ovf_base = ws->ovf_base; sa.ovf_cap = ws->ovf_cap;
+    ws->emit_segmented = true;   // (cleared again below if the scan has to take the walk kernel)
+  }
   const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
   if (prof) {
     if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
@@ -158,6 +180,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
       sa.text = ws->aux_a + a0;
       e = launch_filter(a->dev, sa, mode, st);
     } else {
+      ws->emit_segmented = false;
       e = launch_walk(a->dev, sa, mode, st);
     }
   } else {
@@ -176,24 +199,64 @@ static int read_scalars(Workspace* ws, cudaStream_t st) {
   return AM_OK;
 }
 
-// Scan in EMIT mode and sort; on return ws->keys_b[0..*n) holds the sorted keys.
-int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n) {
+// Scan in EMIT mode and order the keys; on return ws->keys_b[0..*n) holds the sorted keys.
+//  * filter kernel: the keys arrive in per-segment slots; bases = prefix sums of the fills; one local rank sort per segment
+//    puts every key into its final place.  If some segment overflowed, segments + overflow area are compacted and
+//    radix-sorted instead; if even the overflow area was too small the buffers grow and the scan runs again.
+//  * walk kernel: global append + radix sort.
+int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked) {
+  if (unpacked) *unpacked = false;
   uint64_t span = t.text_len - std::min(t.report_begin, t.text_len);
   int rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
   if (rc) return rc;
+  const int end_bit = std::min(64, bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits);
   for (int attempt = 0;; attempt++) {
     rc = launch_scan(a, ws, t, MODE_EMIT, st);
     if (rc) return rc;
+    const uint64_t cap = ws->keys_a_bytes / 8;
+    if (ws->emit_segmented) {
+      const size_t stb = seg_scan_temp_bytes(ws->num_segs);
+      if ((rc = ws->need_sort_temp(stb))) return rc;
+      cudaError_t e = launch_seg_scan(ws->sort_temp, stb, ws->seg_counts, ws->num_segs, ws->seg_cap, ws->seg_bases, st);
+      if (e == cudaSuccess)   // d_scalars[8..16): number of keys stored in the segments
+        e = cudaMemcpyAsync(ws->d_scalars + 8, ws->seg_bases + ws->num_segs, 8, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "segment scan");
+      // queued before the host knows whether a segment overflowed (the common case: none did, and then this was the last
+      // kernel of the call -- one host round trip in total); after an overflow its output is simply overwritten below
+      e = launch_seg_sort(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_b, matches, matches_cap, a->host.rank_bits, a->dev.id_of_rank, st);
+      if (e != cudaSuccess) return cuda_fail(e, "segment sort");
+      rc = read_scalars(ws, st);
+      if (rc) return rc;
+      const uint64_t n_ovf = *reinterpret_cast<uint64_t*>(ws->h_scalars), stored = *reinterpret_cast<uint64_t*>(ws->h_scalars + 8);
+      *n = stored + n_ovf;
+      if (n_ovf == 0) {
+        if (unpacked && matches) *unpacked = true;
+        return AM_OK;
+      }
+      if (n_ovf <= ws->ovf_cap && *n <= ws->keys_b_bytes / 8) {
+        e = launch_seg_compact(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_a + ws->ovf_base, n_ovf, stored, ws->keys_b, st);
+        if (e != cudaSuccess) return cuda_fail(e, "segment compaction");
+        size_t tb = sort_temp_bytes(*n, end_bit);
+        if ((rc = ws->need_sort_temp(tb))) return rc;
+        e = sort_keys(ws->sort_temp, tb, ws->keys_b, ws->keys_a, *n, end_bit, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ws->keys_b, ws->keys_a, *n * 8, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "radix sort");
+        return AM_OK;
+      }
+      if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
+      rc = ws->need_keys(2 * *n + 1024);   // half of the buffer is the overflow area: now it holds every key
+      if (rc) return rc;
+      continue;
+    }
     rc = read_scalars(ws, st);
     if (rc) return rc;
     *n = *reinterpret_cast<uint64_t*>(ws->h_scalars);
-    if (*n <= ws->keys_a_bytes / 8) break;
+    if (*n <= cap) break;
     if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
     rc = ws->need_keys(*n);  // exact size is now known: rescan
     if (rc) return rc;
   }
   if (*n == 0) return AM_OK;
-  const int end_bit = std::min(64, bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits);
   size_t tb = sort_temp_bytes(*n, end_bit);
   rc = ws->need_sort_temp(tb);
   if (rc) return rc;
@@ -350,11 +413,12 @@ int am_find_all_dev(const am_automaton* a, am_dev_text t, void* stream, am_match
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t n = 0;
-  rc = find_all_sorted(a, ws, t, st, &n);
+  bool unpacked = false;
+  rc = find_all_sorted(a, ws, t, st, &n, dev_out, dev_out ? cap : 0, &unpacked);
   if (!rc) {
     *n_found = n;
     if (n > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
-    else if (n > 0) {
+    else if (n > 0 && !unpacked) {
       if (!dev_out) rc = fail(AM_E_BADARG, "dev_out is null");
       else {
         cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, dev_out, st);

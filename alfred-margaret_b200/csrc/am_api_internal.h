@@ -23,12 +23,17 @@ struct Workspace {
   am_match* matches = nullptr; size_t matches_bytes = 0;
   uint8_t* aux_a = nullptr; size_t aux_a_bytes = 0;   // replacer ping-pong text buffers
   uint8_t* aux_b = nullptr; size_t aux_b_bytes = 0;
+  // segmented emission of the filter kernel (set by launch_scan in EMIT mode; emit_segmented = false: global append, e.g. walk kernel)
+  uint32_t* seg_counts = nullptr; size_t seg_counts_bytes = 0;
+  uint64_t* seg_bases = nullptr; size_t seg_bases_bytes = 0;
+  bool emit_segmented = false; uint64_t num_segs = 0; uint32_t seg_cap = 0; uint64_t ovf_base = 0, ovf_cap = 0;
   ~Workspace();
   int need_keys(uint64_t n);
   int need_sort_temp(size_t bytes);
   int need_text(uint64_t n);
   int need_matches(uint64_t n);
   int need_aux(uint64_t a_bytes, uint64_t b_bytes);
+  int need_segs(uint64_t n);
 };
 
 extern thread_local std::string g_last_error;
@@ -40,7 +45,10 @@ int check_ready(const struct ::am_automaton* a);
 Workspace* acquire_ws(const struct ::am_automaton* a);
 void release_ws(const struct ::am_automaton* a, Workspace* w);
 int launch_scan(const struct ::am_automaton* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st);
-int find_all_sorted(const struct ::am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n);
+// `matches` (nullable, device): when the keys could be ordered by the per-segment sort, the am_match records are written
+// in the same kernel and *unpacked is set; otherwise the caller unpacks ws->keys_b itself.
+int find_all_sorted(const struct ::am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n,
+                    am_match* matches = nullptr, uint64_t matches_cap = 0, bool* unpacked = nullptr);
 int lower_utf8_host(const LowerTable& lt, const uint8_t* in, int64_t len, std::vector<uint8_t>* out);
 
 }  // namespace am

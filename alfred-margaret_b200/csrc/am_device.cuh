@@ -46,6 +46,9 @@ struct ScanArgs {
   unsigned long long* d_count;  // COUNT: matches; EMIT: keys produced (may exceed cap)
   uint64_t* d_keys;             // EMIT: (pos << rank_bits | rank)
   uint64_t cap;
+  // filter kernel, EMIT: keys go into per-segment slots of d_keys (segment = 2^seg_shift bytes of end positions, seg_cap
+  // slots each, counters in seg_counts); keys of a full segment go to d_keys[ovf_base ..) and are counted in d_count
+  uint32_t* seg_counts; uint32_t seg_shift, seg_cap; uint64_t ovf_base, ovf_cap;
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)

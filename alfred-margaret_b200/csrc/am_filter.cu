@@ -36,7 +36,6 @@ constexpr int FK_CHUNK = FK_PAIRS * 1024;        // bytes per warp chunk
 constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
 constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
 constexpr int FK_SQ = 64;                        // survivor queue entries per warp
-constexpr int FK_WSTAGE = 32;                    // staged match keys per warp
 constexpr uint64_t FK_SPAN = 1ull << 40;         // bytes per launch (one launch per scan in practice; survivors carry 64-bit offsets)
 // Build-time variants (A/B-tested on the GPU; the rejected ones -- warp-scan compaction of the candidates, bulk L2
 // prefetch, IMAD.HI row addressing, an out-of-line survivor drain -- are recorded in profiles/README.md):
@@ -51,9 +50,7 @@ struct FilterSmem {
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
   unsigned long long sq_pos[FK_WARPS][FK_SQ];    // 16 KiB: survivor queue, offset from v_begin ...
   uint32_t sq_g[FK_WARPS][FK_SQ];                //  8 KiB: ... and its q-gram
-  unsigned long long wkeys[FK_WARPS][FK_WSTAGE]; // 8 KiB
   uint32_t sq_n[FK_WARPS];
-  uint32_t wkeys_n[FK_WARPS];
   unsigned long long red[FK_WARPS];
   alignas(8) unsigned long long mbar;
 };
@@ -66,27 +63,17 @@ struct FilterCtx {
       : v_begin(vb), a0((uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15)), warp(threadIdx.x >> 5), lane(threadIdx.x & 31) {}
 };
 
-template <int MODE>
-__device__ __forceinline__ void fk_emit(const ScanArgs& a, FilterSmem* sm, uint32_t warp, unsigned long long key) {
-  const uint32_t i = atomicAdd(&sm->wkeys_n[warp], 1u);
-  if (i < FK_WSTAGE) { sm->wkeys[warp][i] = key; return; }
-  const unsigned long long g = atomicAdd(a.d_count, 1ull);  // stage full: direct append
-  if (g < a.cap) a.d_keys[g] = key;
-}
-
-// Flush the warp's staged keys (call with the warp converged).
-__device__ __forceinline__ void fk_flush(const ScanArgs& a, FilterSmem* sm, uint32_t warp, uint32_t lane, uint32_t min_fill) {
-  __syncwarp();
-  uint32_t n = sm->wkeys_n[warp];
-  if (n > FK_WSTAGE) n = FK_WSTAGE;
-  if (n < min_fill || n == 0) return;
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(a.d_count, (unsigned long long)n);
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
-  if (lane < n && base + lane < a.cap) a.d_keys[base + lane] = sm->wkeys[warp][lane];
-  __syncwarp();
-  if (lane == 0) sm->wkeys_n[warp] = 0;
-  __syncwarp();
+// Emit one match.  The key goes into the SEGMENT of its end position (128 KiB of text per segment, a fixed number of
+// slots each; slot reserved with an atomic on the segment's own counter), so the list comes out ordered at segment
+// granularity and a local rank sort per segment replaces the global radix sort (seg_sort_kernel).  A key whose
+// segment is full goes to the overflow area; any overflow sends the host down the compact + radix sort path.
+__device__ __forceinline__ void fk_emit(const DevAutomaton& A, const ScanArgs& a, uint64_t end, uint32_t rank) {
+  const unsigned long long key = ((unsigned long long)(end + a.pos_base) << A.rank_bits) | rank;
+  const uint32_t seg = (uint32_t)((end - a.report_begin - 1) >> a.seg_shift);
+  const uint32_t slot = atomicAdd(a.seg_counts + seg, 1u);
+  if (slot < a.seg_cap) { a.d_keys[(uint64_t)seg * a.seg_cap + slot] = key; return; }
+  const unsigned long long o = atomicAdd(a.d_count, 1ull);   // EMIT: d_count counts the overflowed keys
+  if (o < a.ovf_cap) a.d_keys[a.ovf_base + o] = key;
 }
 
 // Walk the goto trie from a survivor (its q-gram is a prefix of some needle, or a rare T2 alias):
@@ -125,13 +112,13 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
         if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
         if (s.w & JUMP_SINGLE) {
           if (MODE == MODE_COUNT) local_count += 1;
-          else fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | s.y);
+          else fk_emit(A, a, end, s.y);
         } else {                                           // duplicates of one needle: all ranks of the leaf
           const uint32_t olo = __ldg(A.own_off + s.y), ohi = __ldg(A.own_off + s.y + 1);
           if (MODE == MODE_COUNT) local_count += ohi - olo;
           else
             for (uint32_t j = olo; j < ohi; j++)
-              fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+              fk_emit(A, a, end, __ldg(A.own_rank + j));
         }
         return;
       }
@@ -152,7 +139,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
         else if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
         else
           for (uint32_t j = olo; j < ohi; j++)
-            fk_emit<MODE>(a, sm, c.warp, ((unsigned long long)(end + a.pos_base) << A.rank_bits) | __ldg(A.own_rank + j));
+            fk_emit(A, a, end, __ldg(A.own_rank + j));
       }
     }
     if (i + d >= a.text_len) return;
@@ -173,7 +160,6 @@ __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanA
   __syncwarp();
   if (c.lane == 0) sm->sq_n[c.warp] = 0;
   __syncwarp();
-  if (MODE == MODE_EMIT) fk_flush(a, sm, c.warp, c.lane, FK_WSTAGE / 2);
 }
 
 
@@ -322,7 +308,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
                    "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
   }
-  if (lane == 0) { sm->sq_n[warp] = 0; sm->wkeys_n[warp] = 0; }
+  if (lane == 0) sm->sq_n[warp] = 0;
   __syncthreads();
   {
     uint32_t done = 0;
@@ -425,7 +411,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
     }
   }
   fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
-  if (MODE == MODE_EMIT) fk_flush(a, sm, warp, lane, 1);
 
   if (MODE == MODE_COUNT) {
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);

@@ -17,6 +17,8 @@
 // Both produce (end_pos << rank_bits | rank) keys; sorting them restores the reference's
 // callback order (end_pos ascending, then longest needle / later duplicate first).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "am_device.cuh"
 #include "am_kernels.h"
@@ -438,6 +440,93 @@ cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t te
   const unsigned blocks = (unsigned)std::min<uint64_t>((nvec + 255) / 256, (uint64_t)sm_count() * 16);
   g_kernel_launches++;
   lower_kernel<<<blocks, 256, 0, st>>>(A, text, text_len, out, exceptions, keep ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// segmented emission of the filter kernel -> ordered key list
+// =====================================================================================================
+// bases[s] = sum of min(count, seg_cap) over s' < s, for s = 0 .. num_segs (the last one is the total): one CUB scan.
+struct SegClamp {
+  uint32_t cap;
+  __host__ __device__ unsigned long long operator()(uint32_t c) const { return c < cap ? c : cap; }
+};
+
+// One warp per segment: rank sort of its (distinct) keys straight into their final place.
+constexpr int SEG_SORT_WARPS = 8;
+__global__ void __launch_bounds__(SEG_SORT_WARPS * 32) seg_sort_kernel(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs,
+                                                                       uint32_t seg_cap, uint64_t* out, am_match* matches, uint64_t matches_cap,
+                                                                       uint32_t rank_bits, const uint32_t* id_of_rank) {
+  __shared__ unsigned long long sk[SEG_SORT_WARPS][SEG_CAP_MAX];
+  auto place = [&](uint64_t at, unsigned long long k) {         // final position of key k (and, fused, its am_match record)
+    out[at] = k;
+    if (matches && at < matches_cap) {
+      am_match mm;
+      mm.end_pos = k >> rank_bits; mm.needle_id = __ldg(id_of_rank + (uint32_t)(k & ((1ull << rank_bits) - 1))); mm.reserved = 0;
+      matches[at] = mm;
+    }
+  };
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint64_t s = (uint64_t)blockIdx.x * SEG_SORT_WARPS + warp; s < num_segs; s += (uint64_t)gridDim.x * SEG_SORT_WARPS) {
+    uint32_t c = seg_counts[s]; if (c > seg_cap) c = seg_cap;
+    if (c == 0) continue;
+    const uint64_t* src = seg_keys + s * seg_cap;
+    const uint64_t base = bases[s];
+    if (c <= 32) {                                             // the common case: one key per lane, ranks by shuffles
+      const unsigned long long k = lane < c ? src[lane] : ~0ull;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < c; j++) rank += __shfl_sync(0xFFFFFFFFu, k, j) < k;
+      if (lane < c) place(base + rank, k);
+    } else {
+      __syncwarp();
+      for (uint32_t i = lane; i < c; i += 32) sk[warp][i] = src[i];
+      __syncwarp();
+      for (uint32_t i = lane; i < c; i += 32) {
+        const unsigned long long k = sk[warp][i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < c; j++) rank += sk[warp][j] < k;
+        place(base + rank, k);
+      }
+    }
+  }
+}
+
+// Some key overflowed its segment: gather the segments and the overflow area into one unordered list for the radix sort.
+__global__ void seg_compact_kernel(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs, uint32_t seg_cap,
+                                   const uint64_t* ovf_keys, uint64_t n_ovf, uint64_t stored_total, uint64_t* out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t s = warp; s < num_segs; s += nwarps) {
+    uint32_t c = seg_counts[s]; if (c > seg_cap) c = seg_cap;
+    for (uint32_t i = lane; i < c; i += 32) out[bases[s] + i] = seg_keys[s * seg_cap + i];
+  }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ovf; i += (uint64_t)gridDim.x * blockDim.x) out[stored_total + i] = ovf_keys[i];
+}
+
+size_t seg_scan_temp_bytes(uint64_t num_segs) {
+  size_t bytes = 0;
+  auto in = thrust::make_transform_iterator(static_cast<const uint32_t*>(nullptr), SegClamp{0});
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, (unsigned long long*)nullptr, (int64_t)num_segs + 1);
+  return bytes;
+}
+// seg_counts holds num_segs + 1 entries (the last one zero), bases num_segs + 1: bases[num_segs] is the number of stored keys.
+cudaError_t launch_seg_scan(void* temp, size_t temp_bytes, const uint32_t* seg_counts, uint64_t num_segs, uint32_t seg_cap, uint64_t* bases, cudaStream_t st) {
+  auto in = thrust::make_transform_iterator(seg_counts, SegClamp{seg_cap});
+  g_kernel_launches++;
+  return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, reinterpret_cast<unsigned long long*>(bases), (int64_t)num_segs + 1, st);
+}
+cudaError_t launch_seg_sort(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs, uint32_t seg_cap, uint64_t* out,
+                            am_match* matches, uint64_t matches_cap, uint32_t rank_bits, const uint32_t* id_of_rank, cudaStream_t st) {
+  const unsigned blocks = (unsigned)std::min<uint64_t>((num_segs + SEG_SORT_WARPS - 1) / SEG_SORT_WARPS, (uint64_t)sm_count() * 8);
+  g_kernel_launches++;
+  seg_sort_kernel<<<blocks, SEG_SORT_WARPS * 32, 0, st>>>(seg_keys, seg_counts, bases, num_segs, seg_cap, out, matches, matches_cap, rank_bits, id_of_rank);
+  return cudaGetLastError();
+}
+cudaError_t launch_seg_compact(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs, uint32_t seg_cap,
+                               const uint64_t* ovf_keys, uint64_t n_ovf, uint64_t stored_total, uint64_t* out, cudaStream_t st) {
+  const unsigned blocks = (unsigned)std::min<uint64_t>((num_segs * 32 + 255) / 256 + (n_ovf + 255) / 256, (uint64_t)sm_count() * 8);
+  g_kernel_launches++;
+  seg_compact_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(seg_keys, seg_counts, bases, num_segs, seg_cap, ovf_keys, n_ovf, stored_total, out);
   return cudaGetLastError();
 }
 

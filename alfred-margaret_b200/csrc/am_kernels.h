@@ -29,6 +29,17 @@ cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cu
 
 // IgnoreCase front end of the filter kernel: lowered copy of the text (+ count of length-changing code points).
 cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, bool keep, cudaStream_t st);
+// Segmented emission of the filter kernel (ScanArgs::seg_*): bases = exclusive prefix of min(count, seg_cap), bases[num_segs] = their sum;
+// then either every segment is rank-sorted into its final place (no key overflowed), or everything is compacted for the radix sort.
+constexpr uint32_t SEG_SHIFT = 17;            // 128 KiB of end positions per segment
+constexpr uint32_t SEG_CAP_MAX = 256;         // slots per segment at most (the local sort is quadratic in the fill)
+size_t seg_scan_temp_bytes(uint64_t num_segs);
+cudaError_t launch_seg_scan(void* temp, size_t temp_bytes, const uint32_t* seg_counts /* num_segs + 1, last = 0 */, uint64_t num_segs, uint32_t seg_cap,
+                            uint64_t* bases /* num_segs + 1, last = total */, cudaStream_t st);
+cudaError_t launch_seg_sort(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs, uint32_t seg_cap, uint64_t* out,
+                            am_match* matches /* nullable: also unpack into am_match records */, uint64_t matches_cap, uint32_t rank_bits, const uint32_t* id_of_rank, cudaStream_t st);
+cudaError_t launch_seg_compact(const uint64_t* seg_keys, const uint32_t* seg_counts, const uint64_t* bases, uint64_t num_segs, uint32_t seg_cap,
+                               const uint64_t* ovf_keys, uint64_t n_ovf, uint64_t stored_total, uint64_t* out, cudaStream_t st);
 size_t sort_temp_bytes(uint64_t n, int end_bit);
 cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_t* out, uint64_t n, int end_bit, cudaStream_t st);
 cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st);
