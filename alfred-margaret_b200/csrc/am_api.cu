@@ -62,6 +62,9 @@ Workspace::~Workspace() {
   for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases})
     if (p) cudaFree(p);
   if (h_scalars) cudaFreeHost(h_scalars);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (scan_stream) cudaStreamDestroy(scan_stream);
+  for (cudaEvent_t ev : copy_done) if (ev) cudaEventDestroy(ev);
 }
 
 static int ws_grow(void** p, size_t* cap, size_t need, const char* what) {
@@ -447,16 +450,77 @@ static int upload_text(Workspace* ws, const am_u8slice& hay, cudaStream_t st, am
   return AM_OK;
 }
 
+// COUNT / ANY over a host buffer: the text goes up in chunks on a copy stream while the previous chunk is scanned on a
+// second stream (chunk k is scanned with `halo_bytes` of warm-up before it and reports the matches that END inside it,
+// exactly like a shard), so the scan hides behind the PCIe transfer -- and `containsAny` stops uploading at the first
+// chunk that holds a match: the `Done` of the reference's fold (Searcher.hs:156-164) reaches all the way to the bus.
+}  // extern "C" (the chunk loop is a template)
+
+constexpr uint64_t HOST_CHUNK = 64ull << 20;
+// Calls fn(window, stream) for every chunk in order; fn returns < 0 to stop early (no error), 0 to go on, > 0 = error code.
+template <class F>
+static int for_each_host_chunk(const am_automaton* a, Workspace* ws, const am_u8slice& hay, F fn) {
+  const uint64_t len = (uint64_t)hay.len;
+  int rc = ws->need_text(len);
+  if (rc) return rc;
+  if (len <= 2 * HOST_CHUNK) {                                 // small text: one upload, one window
+    am_dev_text t;
+    rc = upload_text(ws, hay, 0, &t);
+    if (!rc) rc = fn(t, (cudaStream_t)0);
+    return rc < 0 ? AM_OK : rc;
+  }
+  if (!ws->copy_stream) {
+    if (cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ws->scan_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ws->copy_done[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ws->copy_done[1], cudaEventDisableTiming) != cudaSuccess)
+      return cuda_fail(cudaGetLastError(), "stream / event creation");
+  }
+  const uint8_t* src = hay.ptr + hay.off;
+  const uint64_t halo = a->host.halo_bytes;
+  const uint64_t chunks = (len + HOST_CHUNK - 1) / HOST_CHUNK;
+  auto upload = [&](uint64_t k) -> cudaError_t {
+    const uint64_t b = k * HOST_CHUNK, e = std::min(len, b + HOST_CHUNK);
+    cudaError_t err = cudaMemcpyAsync(ws->text + b, src + b, e - b, cudaMemcpyHostToDevice, ws->copy_stream);
+    if (err == cudaSuccess) err = cudaEventRecord(ws->copy_done[k & 1], ws->copy_stream);
+    return err;
+  };
+  cudaError_t e = upload(0);
+  for (uint64_t k = 0; k < chunks && e == cudaSuccess; k++) {
+    if (k + 1 < chunks) e = upload(k + 1);                     // in flight while chunk k is scanned
+    if (e != cudaSuccess) break;
+    e = cudaStreamWaitEvent(ws->scan_stream, ws->copy_done[k & 1], 0);
+    if (e != cudaSuccess) break;
+    const uint64_t b = k * HOST_CHUNK, end = std::min(len, b + HOST_CHUNK), w = b > halo ? b - halo : 0;
+    am_dev_text t{ws->text + w, end - w, b - w, w};
+    rc = fn(t, ws->scan_stream);                               // fn synchronises scan_stream before it returns (it reads results back):
+    if (rc) break;                                             // that also orders the reuse of copy_done[k & 1] by chunk k + 2
+  }
+  cudaStreamSynchronize(ws->copy_stream);                      // an early exit leaves one upload in flight: the buffer is reused next call
+  cudaStreamSynchronize(ws->scan_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pipelined upload");
+  return rc < 0 ? AM_OK : rc;
+}
+
+static int scan_host_pipelined(const am_automaton* a, Workspace* ws, const am_u8slice& hay, int mode, uint64_t* out_count, int* out_any) {
+  if (out_count) *out_count = 0;
+  if (out_any) *out_any = 0;
+  return for_each_host_chunk(a, ws, hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
+    int rc = launch_scan(a, ws, t, mode, st);
+    if (!rc) rc = read_scalars(ws, st);
+    if (rc) return rc;
+    if (out_count) *out_count += *reinterpret_cast<uint64_t*>(ws->h_scalars);
+    if (out_any && *reinterpret_cast<int*>(ws->h_scalars + 8) != 0) { *out_any = 1; return -1; }
+    return 0;
+  });
+}
+
+extern "C" {
+
 int am_count_matches(const am_automaton* a, am_u8slice hay, uint64_t* out_count) {
   int rc = check_ready(a); if (rc) return rc;
   if ((rc = check_slice(hay))) return rc;
   if (!out_count) return fail(AM_E_BADARG, "out_count is null");
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  am_dev_text t;
-  rc = upload_text(ws, hay, 0, &t);
-  if (!rc) rc = launch_scan(a, ws, t, MODE_COUNT, 0);
-  if (!rc) rc = read_scalars(ws, 0);
-  if (!rc) *out_count = *reinterpret_cast<uint64_t*>(ws->h_scalars);
+  rc = scan_host_pipelined(a, ws, hay, MODE_COUNT, out_count, nullptr);
   release_ws(a, ws);
   return rc;
 }
@@ -466,11 +530,7 @@ int am_contains_any(const am_automaton* a, am_u8slice hay, int* out_bool) {
   if ((rc = check_slice(hay))) return rc;
   if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  am_dev_text t;
-  rc = upload_text(ws, hay, 0, &t);
-  if (!rc) rc = launch_scan(a, ws, t, MODE_ANY, 0);
-  if (!rc) rc = read_scalars(ws, 0);
-  if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
+  rc = scan_host_pipelined(a, ws, hay, MODE_ANY, nullptr, out_bool);
   release_ws(a, ws);
   return rc;
 }
@@ -480,22 +540,28 @@ int am_find_all(const am_automaton* a, am_u8slice hay, am_match* out, size_t cap
   if ((rc = check_slice(hay))) return rc;
   if (!n_found) return fail(AM_E_BADARG, "n_found is null");
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  am_dev_text t;
-  uint64_t n = 0;
-  rc = upload_text(ws, hay, 0, &t);
-  if (!rc) rc = find_all_sorted(a, ws, t, 0, &n);
-  if (!rc) {
-    *n_found = n;
-    if (n > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
-    else if (n > 0) {
-      if (!out) rc = fail(AM_E_BADARG, "out is null");
-      else if (!(rc = ws->need_matches(n))) {
-        cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, ws->matches, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out, ws->matches, n * sizeof(am_match), cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-        if (e != cudaSuccess) rc = cuda_fail(e, "unpack / D2H");
-      }
+  // chunk by chunk (the lists of consecutive chunks concatenate: matches are partitioned by end position); each chunk's
+  // records travel back while the next chunk is scanned and the one after that is uploaded
+  uint64_t total = 0;
+  rc = for_each_host_chunk(a, ws, hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
+    uint64_t n = 0;
+    int r = find_all_sorted(a, ws, t, st, &n);
+    if (r) return r;
+    if (n > 0 && total + n <= cap) {
+      if (!out) return fail(AM_E_BADARG, "out is null");
+      if ((r = ws->need_matches(n))) return r;
+      cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, ws->matches, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out + total, ws->matches, n * sizeof(am_match), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return cuda_fail(e, "unpack / D2H");
     }
+    total += n;                                              // (keeps counting past `cap`: the caller learns the size it needs)
+    return 0;
+  });
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = cuda_fail(e, "unpack / D2H");
+    *n_found = total;
+    if (!rc && total > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
   }
   release_ws(a, ws);
   return rc;

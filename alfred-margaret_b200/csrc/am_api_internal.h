@@ -26,6 +26,8 @@ struct Workspace {
   // segmented emission of the filter kernel (set by launch_scan in EMIT mode; emit_segmented = false: global append, e.g. walk kernel)
   uint32_t* seg_counts = nullptr; size_t seg_counts_bytes = 0;
   uint64_t* seg_bases = nullptr; size_t seg_bases_bytes = 0;
+  cudaStream_t copy_stream = nullptr, scan_stream = nullptr;   // host-buffer scans: upload chunk k + 1 while chunk k is scanned
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
   bool emit_segmented = false; uint64_t num_segs = 0; uint32_t seg_cap = 0; uint64_t ovf_base = 0, ovf_cap = 0;
   ~Workspace();
   int need_keys(uint64_t n);

@@ -467,3 +467,32 @@ def test_stride2_cells_and_tail_compare(am, oracle, torch_cuda):
             assert got_n == n
             got = out.cpu().numpy()[: 2 * n].view(am.automaton.MATCH_DTYPE)
             assert np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (needles, shift)
+
+
+def test_host_scans_pipelined_in_chunks(am, oracle):
+    """am_count_matches / am_contains_any with HOST buffers upload the text in 64 MiB chunks while the previous chunk is
+    scanned (each chunk like a shard: halo before it, matches that end inside it); containsAny stops at the first chunk
+    with a match.  Matches that straddle the chunk boundaries must be counted exactly once."""
+    from alfred_margaret_b200 import synth
+    needles = synth.random_needles(1000, 42)
+    CH = 64 << 20
+    n = 3 * CH + 12345
+    hay = synth.fill_host(0, n, 7, b"0123456789")                 # no needle byte at all
+    m = machine(am, needles)
+    assert m.count_matches(hay) == 0 and m.contains_any(hay) is False
+    long_needle = max(needles, key=len)
+    spots = [CH - len(long_needle) // 2, 2 * CH - len(long_needle), 2 * CH, 3 * CH - len(long_needle) + 1, n - len(long_needle)]
+    for at in spots:                                              # across / at / next to every chunk boundary, and at the very end
+        hay[at:at + len(long_needle)] = np.frombuffer(long_needle, dtype=np.uint8)
+    want = oracle.Machine(needles).find_all(hay, threads=8, cap=1 << 16)
+    assert len(want) >= len(spots)
+    assert m.count_matches(hay) == len(want)
+    assert m.contains_any(hay) is True
+    got = m.find_all(hay)
+    assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])
+    # IgnoreCase takes the same chunked path (lowered copy per chunk)
+    mi = machine(am, needles, cs=1)
+    up = hay.copy()
+    for at in spots:
+        up[at:at + len(long_needle)] = np.frombuffer(long_needle.upper(), dtype=np.uint8)
+    assert mi.count_matches(up) == len(want) and mi.contains_any(up) is True and m.count_matches(up) == 0
