@@ -57,6 +57,7 @@ SYMBOLS = {
     "am_device_count": (C.c_int, []),
     "am_automaton_build": (C.c_int, [C.POINTER(U8Slice), C.c_size_t, C.c_int, C.POINTER(LowerTable), C.POINTER(Options), C.POINTER(C.c_void_p)]),
     "am_automaton_free": (None, [C.c_void_p]),
+    "am_debug_host_filter": (C.c_int, [C.c_void_p, U8Slice, C.c_uint32, C.c_void_p]),
     "am_automaton_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "am_contains_any": (C.c_int, [C.c_void_p, U8Slice, C.POINTER(C.c_int)]),
     "am_count_matches": (C.c_int, [C.c_void_p, U8Slice, C.POINTER(C.c_uint64)]),

@@ -85,6 +85,14 @@ class AcMachine:
         _ffi.check(_ffi.lib().am_automaton_info(self.handle, C.byref(ns), C.byref(mx), C.byref(halo), C.byref(kind)))
         return {"num_states": ns.value, "max_needle_bytes": mx.value, "halo_bytes": halo.value, "kernel_kind": kind.value}
 
+    def host_filter_flags(self, text, align: int = 0) -> np.ndarray:
+        """Introspection (works on a host image, device=-2): the fast path's q-gram filter evaluated on the host for every
+        start position; bit 0 = shared-memory bitmap passes, bit 1 = second level passes (am_debug_host_filter)."""
+        t = as_text(text)
+        out = np.zeros(max(1, t.len), dtype=np.uint8)
+        _ffi.check(_ffi.lib().am_debug_host_filter(self.handle, t.slice(), align, out.ctypes.data))
+        return out[: t.len]
+
     # ---- raw results (needle indices) -------------------------------------------------------------
     def find_all(self, text) -> np.ndarray:
         """All matches in the reference's callback order as a structured array (end_pos, needle_id)."""

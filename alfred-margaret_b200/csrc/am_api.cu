@@ -385,6 +385,61 @@ int am_automaton_info(const am_automaton* a, uint64_t* num_states, uint64_t* max
   return AM_OK;
 }
 
+// Host model of filter_kernel's two filter levels (am_filter.cu: fk_probe16 / fk_probe16_s2, fk_phase_a) on the host image.
+int am_debug_host_filter(const am_automaton* a, am_u8slice text, uint32_t align, uint8_t* out_flags) {
+  if (!a || !out_flags) return fail(AM_E_BADARG, "null argument");
+  if (text.len < 0 || text.off < 0 || (text.len > 0 && !text.ptr)) return fail(AM_E_BADARG, "bad text slice");
+  const HostAutomaton& H = a->host;
+  if (H.q == 0 || H.filter.empty()) return fail(AM_E_UNSUPPORTED, "this automaton has no q-gram filter");
+  const uint8_t* d = text.ptr + text.off;
+  const uint64_t n = (uint64_t)text.len;
+  auto byte_at = [&](uint64_t i) -> uint32_t { return i < n ? d[i] : 0u; };   // the kernel sees arbitrary bytes beyond the text: any value may only ADD candidates
+  auto gram4 = [&](uint64_t i) -> uint32_t { return byte_at(i) | byte_at(i + 1) << 8 | byte_at(i + 2) << 16 | byte_at(i + 3) << 24; };
+  const bool exact = H.t2_exact != 0;
+  const int copies = filter_copies(H.q, exact);
+  const int rowbits = filter_rowbits(copies);
+  const uint32_t qmask = qgram_mask(H.q);
+  for (uint64_t i = 0; i < n; i++) {
+    uint32_t level1;
+    if (filter_is_s2(H.q)) {
+      // stride-2 cells: an even virtual position p tests cell A of its own 4-gram, the odd position p + 1 cell B
+      const bool odd = ((align + i) & 1) != 0;
+      const uint64_t p = odd ? i - 1 : i;                                   // the even position of the pair (may be "-1": bytes before the text)
+      const uint32_t x = odd ? gram4(i) : gram4(i + 1);                      // the 4-gram at p + 1; its top byte is discarded by the shifted multiplier
+      const uint32_t row = (x * HASH_MUL_S2) >> (32 - rowbits);
+      const uint32_t priv = odd ? byte_at(i + 3) : byte_at(i);              // text[p + 4] resp. text[p]
+      (void)p;
+      level1 = (H.filter[(size_t)row * copies] >> (31u - (priv & 31u))) & 1u;
+    } else {
+      uint32_t row, bit;
+      filter_cell(gram4(i) & qmask, &row, &bit);
+      level1 = (H.filter[(size_t)row * copies] >> bit) & 1u;
+    }
+    const uint32_t g = gram4(i) & qmask;
+    uint32_t level2 = 0;
+    if (exact) {
+      uint32_t hb = t2_bucket(g);
+      for (;;) {
+        const uint32_t* slot = H.filter2.data() + 4 * (size_t)hb;
+        uint32_t aux = 0; bool hit = false;
+        if (slot[0] == g) { aux = slot[1]; hit = true; } else if (slot[2] == g) { aux = slot[3]; hit = true; }
+        if (hit) { level2 = (aux & T2_AUX_ANY) ? 1u : (byte_at(i + H.q) == (aux & 0xFFu)); break; }
+        if (!(slot[3] & T2_AUX_OVERFLOW)) break;
+        hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
+      }
+    } else if (H.q == 4) {
+      const uint32_t nb = byte_at(i + 4);
+      const uint32_t ba = t2a_bit(g), bb = t2b_bit(g, nb), bc = t2c_bit(g, nb);
+      level2 = ((H.filter2[T2A_WORD0 + (ba >> 5)] >> (ba & 31)) | ((H.filter2[T2B_WORD0 + (bb >> 5)] >> (bb & 31)) & (H.filter2[T2C_WORD0 + (bc >> 5)] >> (bc & 31)))) & 1u;
+    } else {
+      const uint32_t b2 = filter2_bit(g);
+      level2 = (H.filter2[b2 >> 5] >> (b2 & 31)) & 1u;
+    }
+    out_flags[i] = (uint8_t)(level1 | (level2 << 1));
+  }
+  return AM_OK;
+}
+
 // ---- device-resident entry points -------------------------------------------------------------------------
 int am_count_matches_dev(const am_automaton* a, am_dev_text t, void* stream, uint64_t* out_count) {
   int rc = check_ready(a); if (rc) return rc;

@@ -98,6 +98,12 @@ void am_automaton_free(am_automaton *a);
 /* Introspection (used by tests and by the shard planner). */
 int am_automaton_info(const am_automaton *a, uint64_t *num_states, uint64_t *max_needle_bytes,
                       uint64_t *halo_bytes, int *kernel_kind);
+/* Introspection (host image only, no device): the q-gram filter of the fast path evaluated on the host for every start
+ * position of `text`, exactly as filter_kernel evaluates it for a text whose device address is `align` (0..15) modulo
+ * 16.  out_flags[i] bit 0: the shared-memory bitmap passes position i; bit 1: the second level passes it too.  The
+ * filter may pass positions that start no needle, never the reverse -- the property the CPU tests check.  Returns
+ * AM_E_UNSUPPORTED when the automaton has no filter (empty needle). */
+int am_debug_host_filter(const am_automaton *a, am_u8slice text, uint32_t align, uint8_t *out_flags);
 
 /* ---- host-buffer entry points (the drop-in calls; H2D/D2H inside) -------------------------
  * Searcher.containsAny, Searcher.hs:156-164. */

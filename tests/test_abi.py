@@ -147,3 +147,40 @@ def test_benchmark_file_format(golden, tmp_path):
     assert needles == [n.encode() for n in v["needles"]] and hay == v["haystack"].encode("utf-8")
     p.write_bytes(b"a\nb")
     assert ac.read_needle_haystack_file(str(p)) == ([b"a", b"b"], b"")
+
+
+def test_filter_has_no_false_negatives(oracle):
+    """Host model of the fast path's filter (am_debug_host_filter: the same cell / bucket functions the kernel uses, on the
+    host image): every position where the oracle finds a needle START must pass both levels -- for the stride-2 cells at
+    either parity of the device address, for q < 4, for the exact second level and for the closed-4-gram / 5-gram
+    bitmaps of large needle sets, and for needle sets whose prefixes share rows.  The filter may only add candidates."""
+    from alfred_margaret_b200 import automaton, synth
+    rng = np.random.default_rng(5)
+    cases = [
+        ("C2-like, exact second level", synth.random_needles(1000, 42), synth.AZ),
+        ("large set, bitmap second level", synth.random_needles(6000, 43, 4, 12), synth.AZ),
+        ("q = 3", synth.random_needles(300, 44, 3, 8, b"abcdef"), b"abcdef"),
+        ("q = 2", synth.random_needles(40, 45, 2, 6, b"abc"), b"abc"),
+        ("shared prefixes, duplicates", [b"abca", b"abcab", b"abcabc", b"bcab", b"abca", b"cabcabcab", b"aaaa", b"aaaab"], b"abc"),
+        ("bytes with equal low 5 bits, UTF-8", ["aAb!", "!bAa", "Aa!b1", "åbcå", "💩ab", "ab💩", "ßßab"], "aA!b1åß💩"),
+    ]
+    for name, needles, alpha in cases:
+        nb = [n if isinstance(n, bytes) else n.encode("utf-8") for n in needles]
+        if isinstance(alpha, bytes):
+            hay = synth.fill_host(0, 1 << 18, 9, alpha)
+            synth.plant_host(hay, 0, 10, nb, block=512)
+        else:
+            hay = np.frombuffer("".join(alpha[int(i)] for i in rng.integers(0, len(alpha), size=60000)).encode("utf-8"), dtype=np.uint8).copy()
+        m = automaton.AcMachine([(n, i) for i, n in enumerate(nb)], device=-2)
+        assert m.info()["kernel_kind"] == 2, name
+        want = oracle.Machine(nb).find_all(hay, cap=1 << 22)
+        assert len(want) > 100, name
+        starts = np.unique(want["pos"] - np.array([len(nb[v]) for v in want["value"]], dtype=np.int64))
+        for align in (0, 1):
+            flags = m.host_filter_flags(hay, align)
+            missed = starts[(flags[starts] & 3) != 3]
+            assert missed.size == 0, (name, align, missed[:5])
+            rate1, rate2 = float((flags & 1).mean()), float(((flags & 3) == 3).mean())
+            assert rate2 <= rate1 <= 1.0
+            if name.startswith("C2-like"):                      # the filter also has to FILTER: level 1 < 2 %, both levels < 0.4 %
+                assert rate1 < 0.02 and rate2 < 0.004, (rate1, rate2)   # (0.2 % of the positions start a planted needle)
