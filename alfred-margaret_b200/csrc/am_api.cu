@@ -142,6 +142,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
   // EMIT on the filter kernel: keys go into per-segment slots of keys_a (first half) + an overflow area (second half)
   ws->emit_segmented = false;
   sa.seg_counts = nullptr; sa.seg_shift = SEG_SHIFT; sa.seg_cap = 0; sa.ovf_base = 0; sa.ovf_cap = 0;
+  sa.lower_ascii = 0; sa.d_nonascii = nullptr;
   if (mode == MODE_EMIT && a->kernel_kind == 2 && t.text_len > t.report_begin) {
     const uint64_t num_segs = ((t.text_len - t.report_begin) + (1ull << SEG_SHIFT) - 1) >> SEG_SHIFT;
     uint64_t per = (sa.cap / 2) / num_segs;
@@ -165,10 +166,33 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
     // lowering changes their UTF-8 length stay as they are in the copy and are matched by the needle variants
     // the automaton holds for them (am_build.cpp step 1).  Only an automaton that could not take the variants
     // (ic_copy_exact == false) marks them instead and falls back to the exact per-code-point walk.
+    const bool keep = a->host.ic_copy_exact;
+    // One pass first: if the text is pure ASCII (most logs and English text are), lowering is toLowerAscii on the registers
+    // the text streams through anyway -- no lowered copy, one read of the text.  The kernel flags the first byte above
+    // ASCII and stops; the (few microseconds of) work is thrown away and the text takes the lowered-copy path below.
+    static const bool one_pass_off = []() { const char* v = std::getenv("AM_IC_ONE_PASS"); return v && std::atoi(v) == 0; }();
+    // (needle sets beyond the exact second level produce so many candidates that lowering them one by one costs more than
+    // the lowered copy: measured 10 k needles 845 GB/s in one pass vs 922 GB/s in two, 1 k needles 1 776 vs 1 344)
+    if (keep && a->dev.q == 4 && a->dev.t2_exact && t.text_len >= (1u << 20) && !one_pass_off) {
+      int* d_na = reinterpret_cast<int*>(ws->d_scalars + 24);
+      e = cudaMemsetAsync(d_na, 0, 4, st);
+      sa.lower_ascii = 1; sa.d_nonascii = d_na;
+      if (e == cudaSuccess) e = launch_filter(a->dev, sa, mode, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 24, d_na, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "one-pass IgnoreCase scan");
+      if (*reinterpret_cast<int*>(ws->h_scalars + 24) == 0) {
+        if (prof) { cudaEventRecord(g_ev1, st); g_ev_valid = true; }
+        return AM_OK;
+      }
+      sa.lower_ascii = 0; sa.d_nonascii = nullptr;             // not ASCII: start over
+      e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
+      if (e == cudaSuccess && ws->emit_segmented) e = cudaMemsetAsync(ws->seg_counts, 0, (ws->num_segs + 1) * 4, st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    }
     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(t.dev_text) & 15);
     int rc = ws->need_aux(t.text_len + 64, 0);
     if (rc) return rc;
-    const bool keep = a->host.ic_copy_exact;
     unsigned int* d_exc = reinterpret_cast<unsigned int*>(ws->d_scalars + 16);
     unsigned int exceptions = 0;
     e = keep ? cudaSuccess : cudaMemsetAsync(d_exc, 0, 4, st);
@@ -399,20 +423,21 @@ int am_debug_host_filter(const am_automaton* a, am_u8slice text, uint32_t align,
   const int copies = filter_copies(H.q, exact);
   const int rowbits = filter_rowbits(copies);
   const uint32_t qmask = qgram_mask(H.q);
+  const uint32_t fold = H.case_sensitivity == AM_IGNORE_CASE ? FOLD_MASK : 0u;   // IgnoreCase: `text` is the LOWERED text; the probe folds it
   for (uint64_t i = 0; i < n; i++) {
     uint32_t level1;
     if (filter_is_s2(H.q)) {
       // stride-2 cells: an even virtual position p tests cell A of its own 4-gram, the odd position p + 1 cell B
       const bool odd = ((align + i) & 1) != 0;
       const uint64_t p = odd ? i - 1 : i;                                   // the even position of the pair (may be "-1": bytes before the text)
-      const uint32_t x = odd ? gram4(i) : gram4(i + 1);                      // the 4-gram at p + 1; its top byte is discarded by the shifted multiplier
+      const uint32_t x = (odd ? gram4(i) : gram4(i + 1)) | fold;             // the 4-gram at p + 1; its top byte is discarded by the shifted multiplier
       const uint32_t row = (x * HASH_MUL_S2) >> (32 - rowbits);
       const uint32_t priv = odd ? byte_at(i + 3) : byte_at(i);              // text[p + 4] resp. text[p]
       (void)p;
       level1 = (H.filter[(size_t)row * copies] >> (31u - (priv & 31u))) & 1u;
     } else {
       uint32_t row, bit;
-      filter_cell(gram4(i) & qmask, &row, &bit);
+      filter_cell((gram4(i) | fold) & qmask, &row, &bit);
       level1 = (H.filter[(size_t)row * copies] >> bit) & 1u;
     }
     const uint32_t g = gram4(i) & qmask;

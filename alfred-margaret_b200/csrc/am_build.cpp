@@ -369,16 +369,17 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     for (auto& kv : keys) {
       const bool exact = keys.size() <= T2_MAX_EXACT_KEYS;
       const int copies = filter_copies(q, exact);
+      const uint32_t gf = cs == AM_IGNORE_CASE ? (kv.first | (FOLD_MASK & qgram_mask(q))) : kv.first;   // IgnoreCase: cells of the folded q-gram
       if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
         uint32_t ra, ba, rb, bb;
-        filter_cells_s2(kv.first, filter_rowbits(copies), &ra, &ba, &rb, &bb);
+        filter_cells_s2(gf, filter_rowbits(copies), &ra, &ba, &rb, &bb);
         for (int c = 0; c < copies; c++) {
           A->filter[(size_t)ra * copies + c] |= 1u << ba;
           A->filter[(size_t)rb * copies + c] |= 1u << bb;
         }
       } else {
         uint32_t row, bit;
-        filter_cell(kv.first, &row, &bit);
+        filter_cell(gf, &row, &bit);
         for (int c = 0; c < copies; c++) A->filter[(size_t)row * copies + c] |= 1u << bit;
       }
       uint32_t i = jump_hash(kv.first) & A->jump_mask;

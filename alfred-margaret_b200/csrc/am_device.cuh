@@ -49,6 +49,9 @@ struct ScanArgs {
   // filter kernel, EMIT: keys go into per-segment slots of d_keys (segment = 2^seg_shift bytes of end positions, seg_cap
   // slots each, counters in seg_counts); keys of a full segment go to d_keys[ovf_base ..) and are counted in d_count
   uint32_t* seg_counts; uint32_t seg_shift, seg_cap; uint64_t ovf_base, ovf_cap;
+  // filter kernel, IgnoreCase in one pass: lower the ASCII letters while the text streams through the registers; a byte
+  // >= 0x80 anywhere sets *d_nonascii and ends the launch (the host then takes the lowered-copy path instead)
+  uint32_t lower_ascii; int* d_nonascii;
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)
@@ -61,6 +64,12 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {  // streaming 12
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+
+// SWAR toLowerAscii (Utf8.hs:131-135) on the ASCII bytes of a word; bytes >= 0x80 pass through.
+__device__ __forceinline__ uint32_t lower_ascii_word(uint32_t q) {
+  const uint32_t q7 = q & 0x7f7f7f7fu;                       // bit 7 of (c + 0x3f) & ~(c + 0x25) marks 'A'..'Z'
+  return q | ((((q7 + 0x3f3f3f3fu) & ~(q7 + 0x25252525u)) & ~q & 0x80808080u) >> 2);
 }
 
 __device__ __forceinline__ uint32_t lower_cp(const DevAutomaton& A, uint32_t cp) {  // Utf8.hs:145-151

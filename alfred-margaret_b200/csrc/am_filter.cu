@@ -76,6 +76,13 @@ __device__ __forceinline__ void fk_emit(const DevAutomaton& A, const ScanArgs& a
   if (o < a.ovf_cap) a.d_keys[a.ovf_base + o] = key;
 }
 
+// A text byte as the verification must see it: in the one-pass IgnoreCase form (ASCII-only text) lowered on the fly.
+__device__ __forceinline__ uint32_t fk_text_byte(const ScanArgs& a, const uint8_t* p) {
+  uint32_t c = __ldg(p);
+  if (a.lower_ascii && c - 'A' < 26u) c += 0x20u;
+  return c;
+}
+
 // Walk the goto trie from a survivor (its q-gram is a prefix of some needle, or a rare T2 alias):
 // report every needle that is a prefix of text[i..].  No failure links are needed because every
 // start position is tried (failure-less, position-parallel formulation of Aho-Corasick).
@@ -106,7 +113,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
           uint32_t diff = 0;
 #pragma unroll
           for (uint32_t j = 0; j < 4; j++)
-            if (k + j < tl) diff |= (uint32_t)__ldg(tp + k + j) ^ (uint32_t)__ldg(np + k + j);
+            if (k + j < tl) diff |= fk_text_byte(a, tp + k + j) ^ (uint32_t)__ldg(np + k + j);
           if (diff) return;
         }
         if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
@@ -143,7 +150,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
       }
     }
     if (i + d >= a.text_len) return;
-    const uint32_t ch = __ldg(a.text + i + d);
+    const uint32_t ch = fk_text_byte(a, a.text + i + d);
     st = edge_lookup(A, st & ID_MASK, ch);
     if (st == NONE) return;
     d++;
@@ -245,10 +252,11 @@ __device__ __forceinline__ uint32_t fk_probe16_s2(uint32_t filt_lane, uint32_t k
 // Second-level test of one candidate at byte offset `o` of the warp's window: recover the exact q-gram,
 // look it up in T2 (exact keys + the byte that must follow, or a bitmap for large needle sets).
 // win_s / t2_s: shared-space addresses of the warp's window and of T2.
-template <bool Q4, bool T2X>
+template <bool Q4, bool T2X, bool LOWER>
 __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s, uint32_t t2_s, uint32_t o, uint32_t* g_out) {
   const uint32_t wa = win_s + (o & ~3u);
-  const uint32_t lo = lds32(wa), hi = lds32(wa + 4);
+  uint32_t lo = lds32(wa), hi = lds32(wa + 4);
+  if (LOWER) { lo = lower_ascii_word(lo); hi = lower_ascii_word(hi); }   // one-pass IgnoreCase: the window holds the original text
   const uint32_t sh = (o & 3u) * 8u;
   uint32_t g = __funnelshift_r(lo, hi, sh);
   if (!Q4) g &= A.qmask;
@@ -285,7 +293,9 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
   }
 }
 
-template <int MODE, bool Q4, bool T2X>
+// CASE: 0 = CaseSensitive; 1 = IgnoreCase on a lowered copy of the text (probe the case-FOLDED q-gram, see FOLD_MASK);
+//       2 = IgnoreCase in one pass over the original text (ASCII-only text; fold for the probe, toLowerAscii per candidate).
+template <int MODE, bool Q4, bool T2X, int CASE>
 __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_constant__ DevAutomaton A, const __grid_constant__ ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
   FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -351,11 +361,24 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       tail = __ldg(reinterpret_cast<const uint32_t*>(base16 + gt));
     }
   };
-  auto process_pair = [&](const uint4& qa, const uint4& qb, uint32_t tail, uint64_t tile_rel, uint32_t pair_rel) {
+  constexpr bool LOWER = CASE == 2;
+  uint32_t high_bits = 0;                                  // LOWER: OR of everything loaded (bit 7 of a byte = not ASCII)
+  auto process_pair = [&](const uint4& qa_in, const uint4& qb_in, uint32_t tail_in, uint64_t tile_rel, uint32_t pair_rel) {
+    uint4 qa = qa_in, qb = qb_in;
+    uint32_t tail = tail_in;
     // mirror the pair into the window (exact q-gram recovery for the few candidates)
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane), "r"(qa.x), "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane + 512u), "r"(qb.x), "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s + 1024u), "r"(tail) : "memory");
+    if (CASE != 0) {
+      // IgnoreCase automata hold the cells of the case-FOLDED q-grams (every byte | 0x20: an upper-case ASCII letter and its
+      // lower case fold to the same byte; other bytes only lose a bit, which can add candidates but never lose one), so the
+      // probe costs one OR per word here instead of a toLowerAscii per word.  The exact bytes stay in the window.
+      if (LOWER) high_bits |= (qa.x | qa.y | qa.z) | (qa.w | qb.x | qb.y) | (qb.z | qb.w);
+      qa.x |= FOLD_MASK; qa.y |= FOLD_MASK; qa.z |= FOLD_MASK; qa.w |= FOLD_MASK;
+      qb.x |= FOLD_MASK; qb.y |= FOLD_MASK; qb.z |= FOLD_MASK; qb.w |= FOLD_MASK;
+      tail |= FOLD_MASK;
+    }
     const uint32_t w4A = __shfl_sync(0xFFFFFFFFu, lane == 0 ? qb.x : qa.x, (lane + 1) & 31);
     const uint32_t w4B = __shfl_sync(0xFFFFFFFFu, lane == 0 ? tail : qb.x, (lane + 1) & 31);
     uint32_t m = 0;                                        // bit P <-> position P of the lane's 32 (0..15 granule A, 16..31 B)
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       m ^= 1u << P;
       const uint32_t o = (P & 16u) * 31u + P;              // byte offset from the lane's granule A: (P >> 4) * 512 + (P & 15)
       uint32_t g;
-      if (fk_phase_a<Q4, T2X>(A, win_lane, t2_s, o, &g)) {
+      if (fk_phase_a<Q4, T2X, LOWER>(A, win_lane, t2_s, o, &g)) {
 #if FK_DEBUG
         if (a.debug & 2u) { local_count++; continue; }
 #endif
@@ -398,6 +421,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   if (blockIdx.x < num_tiles) load_pair(g_next, cA, cB, tC);
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
+    if (LOWER) {   // a byte above ASCII anywhere: this launch cannot answer; tell the host and stop at the next tile
+      if (__any_sync(0xFFFFFFFFu, (high_bits & 0x80808080u) != 0) && lane == 0) *a.d_nonascii = 1;
+      if (*reinterpret_cast<volatile int*>(a.d_nonascii)) break;
+    }
     const uint64_t tile_rel = tile * FK_TILE;              // this tile, relative to v_begin
     const uint32_t chunk_rel = warp * FK_CHUNK;            // this warp's chunk, relative to the tile
 #pragma unroll 1
@@ -410,6 +437,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       process_pair(nA, nB, tN, tile_rel, chunk_rel + (uint32_t)pair * 1024u + 1024u);
     }
   }
+  if (LOWER && (high_bits & 0x80808080u) != 0) *a.d_nonascii = 1;   // (the data of the last tile)
   fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
 
   if (MODE == MODE_COUNT) {
@@ -424,12 +452,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   }
 }
 
-template <int MODE, bool Q4, bool T2X>
+template <int MODE, bool Q4, bool T2X, int CASE>
 static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   if (a.text_len <= a.report_begin) return cudaSuccess;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4, T2X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
+    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4, T2X, CASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -442,7 +470,7 @@ static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cud
     const uint64_t tiles = (span + FK_TILE - 1) / FK_TILE;
     const uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
     g_kernel_launches++;
-    filter_kernel<MODE, Q4, T2X><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
+    filter_kernel<MODE, Q4, T2X, CASE><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -452,8 +480,16 @@ static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cud
 template <int MODE>
 static cudaError_t launch_filter_m(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   const bool q4 = A.q == 4, x = A.t2_exact != 0;
-  if (q4) return x ? launch_filter_t<MODE, true, true>(A, a, st) : launch_filter_t<MODE, true, false>(A, a, st);
-  return x ? launch_filter_t<MODE, false, true>(A, a, st) : launch_filter_t<MODE, false, false>(A, a, st);
+  if (a.lower_ascii) {                                         // one-pass IgnoreCase (the host only asks for it when q = 4)
+    if (!q4 || !A.ignore_case) return cudaErrorInvalidValue;
+    return x ? launch_filter_t<MODE, true, true, 2>(A, a, st) : launch_filter_t<MODE, true, false, 2>(A, a, st);
+  }
+  if (A.ignore_case) {
+    if (q4) return x ? launch_filter_t<MODE, true, true, 1>(A, a, st) : launch_filter_t<MODE, true, false, 1>(A, a, st);
+    return x ? launch_filter_t<MODE, false, true, 1>(A, a, st) : launch_filter_t<MODE, false, false, 1>(A, a, st);
+  }
+  if (q4) return x ? launch_filter_t<MODE, true, true, 0>(A, a, st) : launch_filter_t<MODE, true, false, 0>(A, a, st);
+  return x ? launch_filter_t<MODE, false, true, 0>(A, a, st) : launch_filter_t<MODE, false, false, 0>(A, a, st);
 }
 
 cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {

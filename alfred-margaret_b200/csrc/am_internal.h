@@ -174,6 +174,9 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
 //   cell A (needle starts at the even position p):      row of (n1, n2, n3), bit chosen by n0
 //   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
 constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
+// IgnoreCase automata: the filter bitmap holds the cells of the case-FOLDED q-grams (every byte | 0x20) and the kernel
+// folds the text the same way before it probes; the second level and the verification work on exact (lowered) bytes.
+constexpr uint32_t FOLD_MASK = 0x20202020u;
 inline void filter_cells_s2(uint32_t g, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
   *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - rowbits);
   *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31

@@ -304,12 +304,6 @@ __global__ void __launch_bounds__(WALK_THREADS, 1) walk_kernel(DevAutomaton A, S
 //    it is left unchanged in the copy, where the variant needles match it -- exact, no second pass;
 //  * keep = 0: it is overwritten with 0xFF bytes (never part of a valid UTF-8 needle) and counted; the host
 //    then falls back to the exact per-code-point walk kernel for that text.
-// SWAR toLowerAscii (Utf8.hs:131-135) on the ASCII bytes of a word; bytes >= 0x80 pass through.
-__device__ __forceinline__ uint32_t lower_ascii_word(uint32_t q) {
-  const uint32_t q7 = q & 0x7f7f7f7fu;                       // bit 7 of (c + 0x3f) & ~(c + 0x25) marks 'A'..'Z'
-  return q | ((((q7 + 0x3f3f3f3fu) & ~(q7 + 0x25252525u)) & ~q & 0x80808080u) >> 2);
-}
-
 __global__ void __launch_bounds__(256) lower_kernel(DevAutomaton A, const uint8_t* text, uint64_t text_len, uint8_t* out /* same misalignment as text */,
                                                     unsigned int* exceptions, int keep) {
   const uintptr_t addr0 = reinterpret_cast<uintptr_t>(text);

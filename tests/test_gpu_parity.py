@@ -496,3 +496,29 @@ def test_host_scans_pipelined_in_chunks(am, oracle):
     for at in spots:
         up[at:at + len(long_needle)] = np.frombuffer(long_needle.upper(), dtype=np.uint8)
     assert mi.count_matches(up) == len(want) and mi.contains_any(up) is True and m.count_matches(up) == 0
+
+
+def test_ignore_case_one_pass_on_ascii_text(am, oracle, lower_dense, torch_cuda):
+    """runLower on the filter kernel: a text of >= 1 MiB is first scanned in ONE pass that lowers ASCII letters in the
+    registers (no lowered copy); the first byte above ASCII anywhere -- here: only in the very last granule -- makes the
+    kernel give up and the text takes the lowered-copy path.  Both must equal the oracle's runLower."""
+    from alfred_margaret_b200 import synth
+    needles = synth.random_needles(1000, 42)
+    n = (4 << 20) + 123
+    hay = synth.fill_host(0, n, 43, synth.AZ + synth.AZ.upper() + b" .,0123456789")
+    synth.plant_host(hay, 0, 44, [x.upper() if i % 2 else x for i, x in enumerate(needles)], block=2048)
+    om = oracle.Machine(needles)
+    m = machine(am, needles, cs=1)
+    assert m.info()["kernel_kind"] == 2
+    for variant in ("ascii", "one code point above ASCII at the end", "one in the middle"):
+        h = hay.copy()
+        if variant != "ascii":
+            at = n - 9 if "end" in variant else n // 2
+            h[at:at + 2] = np.frombuffer("É".encode("utf-8"), dtype=np.uint8)
+        want = om.find_all(h, cs=1, lower=lower_dense, cap=1 << 20)
+        assert len(want) > 1000
+        got = m.find_all(h)
+        assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), variant
+        assert m.count_matches(h) == len(want) and m.contains_any(h) is True
+        dev = torch_cuda.from_numpy(h).cuda()                      # device-resident, unaligned
+        assert m.count_matches_dev(dev.data_ptr() + 3, n - 3) == len(om.find_all(h[3:], cs=1, lower=lower_dense, cap=1 << 20))
