@@ -77,16 +77,17 @@ __device__ __forceinline__ void fk_emit(const DevAutomaton& A, const ScanArgs& a
 }
 
 // A text byte as the verification must see it: in the one-pass IgnoreCase form (ASCII-only text) lowered on the fly.
-__device__ __forceinline__ uint32_t fk_text_byte(const ScanArgs& a, const uint8_t* p) {
+template <bool LOWER>
+__device__ __forceinline__ uint32_t fk_text_byte(const uint8_t* p) {
   uint32_t c = __ldg(p);
-  if (a.lower_ascii && c - 'A' < 26u) c += 0x20u;
+  if (LOWER && c - 'A' < 26u) c += 0x20u;
   return c;
 }
 
 // Walk the goto trie from a survivor (its q-gram is a prefix of some needle, or a rare T2 alias):
 // report every needle that is a prefix of text[i..].  No failure links are needed because every
 // start position is tried (failure-less, position-parallel formulation of Aho-Corasick).
-template <int MODE>
+template <int MODE, bool LOWER>
 __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
                                                uint64_t v_rel, uint32_t g, unsigned long long& local_count) {
   const uint64_t v = c.v_begin + v_rel;
@@ -113,7 +114,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
           uint32_t diff = 0;
 #pragma unroll
           for (uint32_t j = 0; j < 4; j++)
-            if (k + j < tl) diff |= fk_text_byte(a, tp + k + j) ^ (uint32_t)__ldg(np + k + j);
+            if (k + j < tl) diff |= fk_text_byte<LOWER>(tp + k + j) ^ (uint32_t)__ldg(np + k + j);
           if (diff) return;
         }
         if (MODE == MODE_ANY) { *a.d_flag = 1; return; }
@@ -150,7 +151,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
       }
     }
     if (i + d >= a.text_len) return;
-    const uint32_t ch = fk_text_byte(a, a.text + i + d);
+    const uint32_t ch = fk_text_byte<LOWER>(a.text + i + d);
     st = edge_lookup(A, st & ID_MASK, ch);
     if (st == NONE) return;
     d++;
@@ -158,11 +159,11 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
 }
 
 // Drain the warp's survivor queue (warp converged on entry and exit).
-template <int MODE>
+template <int MODE, bool LOWER>
 __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, const FilterCtx& c,
                                            unsigned long long& local_count, uint32_t n) {
   for (uint32_t k = c.lane; k < n; k += 32) {
-    fk_deep_verify<MODE>(A, a, sm, c, sm->sq_pos[c.warp][k], sm->sq_g[c.warp][k], local_count);
+    fk_deep_verify<MODE, LOWER>(A, a, sm, c, sm->sq_pos[c.warp][k], sm->sq_g[c.warp][k], local_count);
   }
   __syncwarp();
   if (c.lane == 0) sm->sq_n[c.warp] = 0;
@@ -170,14 +171,14 @@ __device__ __forceinline__ void fk_drain_body(const DevAutomaton& A, const ScanA
 }
 
 
-template <int MODE>
+template <int MODE, bool LOWER>
 __device__ __forceinline__ void fk_drain(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint64_t v_begin,
                                          unsigned long long& local_count, uint32_t min_fill) {
   __syncwarp();
   uint32_t n = sm->sq_n[threadIdx.x >> 5];
   if (n > FK_SQ) n = FK_SQ;
   if (n < min_fill || n == 0) return;
-  fk_drain_body<MODE>(A, a, sm, FilterCtx(a, v_begin), local_count, n);
+  fk_drain_body<MODE, LOWER>(A, a, sm, FilterCtx(a, v_begin), local_count, n);
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -407,10 +408,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
         const uint64_t rel = tile_rel + (pair_rel + o + (lane << 4));
         const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
         if (qi < FK_SQ) { sm->sq_pos[warp][qi] = rel; sm->sq_g[warp][qi] = g; }
-        else fk_deep_verify<MODE>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
+        else fk_deep_verify<MODE, LOWER>(A, a, sm, FilterCtx(a, v_begin), rel, g, local_count);   // queue full: verify in place
       }
     }
-    fk_drain<MODE>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
+    fk_drain<MODE, LOWER>(A, a, sm, v_begin, local_count, FK_DRAIN_AT);       // only when a full round of survivors waits
   };
 
   static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
     }
   }
   if (LOWER && (high_bits & 0x80808080u) != 0) *a.d_nonascii = 1;   // (the data of the last tile)
-  fk_drain<MODE>(A, a, sm, v_begin, local_count, 1);
+  fk_drain<MODE, LOWER>(A, a, sm, v_begin, local_count, 1);
 
   if (MODE == MODE_COUNT) {
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
