@@ -1,21 +1,22 @@
-// am_kernels.cu -- sm_100a scan kernels of libam_b200.
+// am_kernels.cu -- sm_100a kernels of libam_b200 other than the q-gram filter scan (am_filter.cu).
 //
-// Replaces the inner loop of `runWithCase` (src/Data/Text/AhoCorasick/Automaton.hs:442-534):
+// The library replaces the inner loop of `runWithCase` (src/Data/Text/AhoCorasick/Automaton.hs:442-534):
 // consumeInput / followCodePoint / lookupTransition / collectMatches.  Two formulations:
 //
-//   walk_kernel    every thread walks one text segment (plus a halo of max-needle-length - 1
+//   walk_kernel    (this file) every thread walks one text segment (plus a halo of max-needle-length - 1
 //                  bytes of warm-up) through the byte-level goto+failure automaton and reports
 //                  the matches that END inside its segment.  General: handles empty needles,
 //                  IgnoreCase (decode -> Char.toLower table -> re-encode on the fly), any density.
 //
-//   filter_kernel  position-parallel: every text position is tested against a q-gram membership
-//                  bitmap held in shared memory (one private copy per bank => conflict-free),
-//                  staged there by TMA bulk copies; the few surviving positions are compacted
-//                  with warp scans into per-warp queues and verified by walking the failure-less
-//                  goto trie.  The haystack is read once from HBM with 128-bit streaming loads.
+//   filter_kernel  (am_filter.cu) position-parallel: every text position is tested against a q-gram membership
+//                  bitmap held in shared memory, staged there by TMA bulk copies -- one probe per two positions;
+//                  the few surviving positions pass an exact second level and are verified against the
+//                  failure-less goto trie.  The haystack is read once from HBM with 128-bit streaming loads.
 //
-// Both produce (end_pos << rank_bits | rank) keys; sorting them restores the reference's
-// callback order (end_pos ascending, then longest needle / later duplicate first).
+// Both produce (end_pos << rank_bits | rank) keys; ordering them restores the reference's callback order
+// (end_pos ascending, then longest needle / later duplicate first).  Also here: lower_kernel (IgnoreCase front
+// end: the lowered copy of the text), the segment scan / sort / compaction that orders the filter kernel's keys
+// without a global sort, the radix sort for the walk kernel's keys, unpack_kernel (key -> am_match).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
