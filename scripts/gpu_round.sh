@@ -13,5 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_kernel -s 2 -c 1 -o $O/${TAG}_filter_emit -f python scripts/prof_one.py 2147483648 find_all > $O/ncu_emit.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:filter_kernel -s 1 -c 1 -o $O/${TAG}_filter_count -f python scripts/prof_one.py 2147483648 count > $O/ncu_count.log 2>&1
 python scripts/perf_configs.py > $O/perf_configs_$TAG.log 2>&1
-timeout 900 python scripts/full_configs.py > $O/full_configs_$TAG.json 2> $O/full_configs_$TAG.err
+timeout 900 python tests/full_configs.py > $O/full_configs_$TAG.json 2> $O/full_configs_$TAG.err
 cat $O/pytest_$TAG.log $O/bench_ref_$TAG.json $O/bench_$TAG.json; tail -3 $O/ncu_emit.log; cat $O/perf_configs_$TAG.log $O/full_configs_$TAG.json

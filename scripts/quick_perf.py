@@ -1,7 +1,7 @@
 """Quick device-resident timing of the scan kernels (development aid; bench.py is the contract)."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [os.path.join(ROOT, "alfred-margaret_b200"), os.path.join(ROOT, "oracle")]
+sys.path[:0] = [os.path.join(ROOT, "alfred-margaret_b200")]
 import torch
 from alfred_margaret_b200 import automaton, synth
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1 << 30
