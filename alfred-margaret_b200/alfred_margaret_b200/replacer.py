@@ -94,3 +94,33 @@ def run_with_limit(r: Replacer, max_length: int, text) -> Optional[bytes]:
 def run(r: Replacer, text) -> bytes:
     """`run = fromJust . runWithLimit replacer maxBound` (:200-201)."""
     return run_with_limit(r, MAX_BOUND, text)
+
+
+# ---- aeson-compatible JSON (generic instances of `Replacer` and `Payload`, :56-83) -----------------------------------
+def to_json(r: Replacer) -> dict:
+    """`Replacer { replacerSearcher :: Searcher Payload }` with the generic encodings: the searcher object of
+    Searcher.hs:68-73 whose values are `Payload` records.  The stored needles are the ones the automaton holds
+    (lowered for IgnoreCase, :105-107); the lengths are those of the ORIGINAL needle (:111-113)."""
+    from .utf8 import lower_utf8
+    needles = []
+    for i, (n, rep) in enumerate(r._replaces):
+        stored = lower_utf8(n, r._lower) if r._case == CaseSensitivity.IgnoreCase else n
+        needles.append([stored.decode("utf-8"), {"needlePriority": -i, "needleLengthBytes": len(n),
+                                                 "needleLengthCodePoints": len(n.decode("utf-8")), "needleReplacement": rep.decode("utf-8")}])
+    return {"replacerSearcher": {"needles": needles, "caseSensitivity": r._case.name}}
+
+
+def from_json(obj: dict, **kw) -> Replacer:
+    """Rebuild from the stored (needle, Payload) pairs.  Priorities must be 0, -1, -2, ... in list order (that is what
+    `build` assigns, :101-111); lowering is idempotent, so the stored needles can go through `build` again."""
+    try:
+        s = obj["replacerSearcher"]
+        case_ = CaseSensitivity[s["caseSensitivity"]]
+        pairs = []
+        for i, (n, payload) in enumerate(s["needles"]):
+            if payload["needlePriority"] != -i:
+                raise ValueError("Replacer: needle %d has priority %r, expected %d" % (i, payload["needlePriority"], -i))
+            pairs.append((n, payload["needleReplacement"]))
+    except (KeyError, TypeError) as e:
+        raise ValueError("Replacer: malformed JSON (%s)" % e)
+    return build(case_, pairs, **kw)

@@ -76,3 +76,21 @@ def contains_any(s: Searcher, text) -> bool:
 def contains_all(s: Searcher, text) -> bool:
     """`containsAll` (:173-187), for searchers from build_needle_id_searcher."""
     return s._automaton.contains_all(text)
+
+
+# ---- aeson-compatible JSON (`instance ToJSON / FromJSON (Searcher v)`, :68-77) -------------------------------------
+def _text(x) -> str:
+    return x if isinstance(x, str) else bytes(x).decode("utf-8")
+
+
+def to_json(s: Searcher, value_to_json=lambda v: [] if v == () else v) -> dict:
+    """`object ["needles" .= needles s, "caseSensitivity" .= caseSensitivity s]`: needles as [text, value] pairs (aeson
+    encodes a tuple as an array and `()` as []), the case as the constructor name."""
+    return {"needles": [[_text(n), value_to_json(v)] for n, v in s._needles], "caseSensitivity": s._case.name}
+
+
+def from_json(obj: dict, value_from_json=lambda j: () if j == [] else j, **kw) -> Searcher:
+    """`buildWithValues <$> o .: "caseSensitivity" <*> o .: "needles"`."""
+    if not isinstance(obj, dict) or "needles" not in obj or "caseSensitivity" not in obj:
+        raise ValueError("Searcher: expected an object with needles and caseSensitivity")
+    return build_with_values(CaseSensitivity[obj["caseSensitivity"]], [(n, value_from_json(v)) for n, v in obj["needles"]], **kw)

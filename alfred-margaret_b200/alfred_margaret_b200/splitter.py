@@ -84,3 +84,14 @@ def split(s: Splitter, text) -> List[bytes]:
 def split_ignore_case(s: Splitter, text) -> List[bytes]:
     """`splitIgnoreCase` (:95-96)."""
     return list(reversed(split_reverse_ignore_case(s, text)))
+
+
+# ---- aeson-compatible JSON (`toJSON = toJSON . separator`, `parseJSON v = build <$> parseJSON v`, :54-60) -----------------
+def to_json(s: Splitter) -> str:
+    return s._sep.decode("utf-8")
+
+
+def from_json(obj, **kw) -> Splitter:
+    if not isinstance(obj, str):
+        raise ValueError("Splitter: expected a JSON string")
+    return build(obj, **kw)
