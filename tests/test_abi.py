@@ -200,3 +200,43 @@ def test_filter_has_no_false_negatives(oracle):
             assert rate2 <= rate1 <= 1.0
             if name.startswith("C2-like"):                      # the filter also has to FILTER: level 1 < 2 %, both levels < 0.4 %
                 assert rate1 < 0.02 and rate2 < 0.004, (rate1, rate2)   # (0.2 % of the positions start a planted needle)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/am_b200.h is the drop-in boundary: it must compile as plain C (no C++, no CUDA or torch types) and a C
+    program must be able to link the library and drive it -- here on a host image (device = -2), without a GPU."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "alfred-margaret_b200", "lib")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "am_b200.h"
+int main(void) {
+  const char *n[3] = {"tshirt", "shirts", "shorts"};
+  am_u8slice needles[3];
+  for (int i = 0; i < 3; i++) { needles[i].ptr = (const uint8_t *)n[i]; needles[i].off = 0; needles[i].len = (int64_t)strlen(n[i]); }
+  am_options opts; memset(&opts, 0, sizeof opts); opts.device = -2;            /* host image only */
+  am_automaton *a = 0;
+  if (am_abi_version() != 1) return 2;
+  if (am_automaton_build(needles, 3, AM_CASE_SENSITIVE, 0, &opts, &a) != AM_OK) { printf("%s\n", am_last_error()); return 3; }
+  uint64_t states = 0, maxlen = 0, halo = 0; int kind = 0;
+  if (am_automaton_info(a, &states, &maxlen, &halo, &kind) != AM_OK) return 4;
+  const char *text = "short tshirts";
+  am_u8slice hay = {(const uint8_t *)text, 0, 13};
+  uint8_t flags[13];
+  if (am_debug_host_filter(a, hay, 0, flags) != AM_OK) return 5;
+  uint64_t cnt = 0;
+  int rc = am_count_matches(a, hay, &cnt);                                      /* no device: must refuse, not fall back */
+  printf("%llu %llu %llu %d %d %d\n", (unsigned long long)states, (unsigned long long)maxlen, (unsigned long long)halo, kind, (flags[6] & 3) == 3, rc == AM_E_NODEVICE);
+  am_automaton_free(a);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lam_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    # 17 states (SURVEY section 8: tshirt 6 + shirts 6 + shorts 4 new + root), longest needle 6, halo 5, filter kernel; "tshirts" starts at 6
+    assert out == ["17", "6", "5", "2", "1", "1"], out
