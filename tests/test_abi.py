@@ -237,6 +237,9 @@ int main(void) {
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
                            "-L", lib_dir, "-lam_b200", "-Wl,-rpath," + lib_dir])
+    # the by-pointer wrappers the Haskell shim imports (GHC cannot pass a struct by value) compile against the same header
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c",
+                           os.path.join(root, "alfred-margaret_b200", "haskell", "cbits", "am_shim.c"), "-o", str(tmp_path / "am_shim.o")])
     out = subprocess.check_output([str(exe)], text=True).split()
     # 17 states (tshirt 6 + shirts 6 + shorts 4 new + root), longest needle 6, halo 5, filter kernel; "tshirts" starts at 6
     assert out == ["17", "6", "5", "2", "1", "1"], out
