@@ -243,3 +243,39 @@ int main(void) {
     out = subprocess.check_output([str(exe)], text=True).split()
     # 17 states (tshirt 6 + shirts 6 + shorts 4 new + root), longest needle 6, halo 5, filter kernel; "tshirts" starts at 6
     assert out == ["17", "6", "5", "2", "1", "1"], out
+
+
+def test_filter_covers_length_changing_variants(oracle, lower_dense):
+    """IgnoreCase on the lowered copy: a code point whose lower case has another UTF-8 length (K U+212A -> k, Å U+212B -> å,
+    ẞ -> ß, İ -> i) stays as it is in the copy, and the automaton holds the needle VARIANTS that match it.  Host model of
+    the filter on such a copy (all other code points already lower case, so the copy is the text itself): every start of
+    an oracle `runLower` match must pass both filter levels -- i.e. the variants reached the bitmap and the second level."""
+    from alfred_margaret_b200 import automaton
+    rng = np.random.default_rng(17)
+    pool = list("kaist") + list("åß")
+    needles = sorted({"".join(rng.choice(pool, size=int(rng.integers(4, 9)))) for _ in range(400)})
+    cps = list("kaist ") * 3 + list("åß") + list("KÅẞİ")
+    hay_s = "".join(rng.choice(cps, size=120000))
+    hay = np.frombuffer(hay_s.encode("utf-8"), dtype=np.uint8).copy()
+    nb = [n.encode("utf-8") for n in needles]
+    want = oracle.Machine(nb).find_all(hay, cs=1, lower=lower_dense, cap=1 << 22)
+    assert len(want) > 500
+    # start of a match = len_cps code points back from its end (makeMatch IgnoreCase, Replacer.hs:271-274)
+    is_lead = (hay & 0xC0) != 0x80
+    lead_index = np.flatnonzero(is_lead)                       # byte offset of every code point
+    cp_of_byte = np.cumsum(is_lead) - 1
+    starts = set()
+    with_variant = 0
+    for pos, v in zip(want["pos"].tolist(), want["value"].tolist()):
+        end_cp = cp_of_byte[pos - 1] + 1
+        s = int(lead_index[end_cp - len(needles[v])])
+        starts.add(s)
+        with_variant += any(c in "KÅẞİ" for c in hay[s:pos].tobytes().decode("utf-8"))
+    assert with_variant > 50                                    # matches that only the variants can produce
+    m = automaton.AcMachine([(n, i) for i, n in enumerate(nb)], case_sensitivity=1, device=-2, force_kernel=2)
+    assert m.info()["kernel_kind"] == 2
+    starts = np.array(sorted(starts), dtype=np.int64)
+    for align in (0, 1):
+        flags = m.host_filter_flags(hay, align)
+        missed = starts[(flags[starts] & 3) != 3]
+        assert missed.size == 0, (align, missed[:5])
