@@ -50,36 +50,56 @@ class DevText(C.Structure):
     _fields_ = [("dev_text", C.c_void_p), ("text_len", C.c_uint64), ("report_begin", C.c_uint64), ("pos_base", C.c_uint64)]
 
 
-# Every symbol include/am_b200.h declares: (restype, argtypes)
+class ShardResult(C.Structure):
+    _fields_ = [("n_local", C.c_uint64), ("global_offset", C.c_uint64), ("total", C.c_uint64)]
+
+
+COMM_ID_BYTES = 128
+_P = C.POINTER
+# Every symbol include/am_b200.h declares: (restype, argtypes).  Structs travel by pointer (ABI version 2).
 SYMBOLS = {
     "am_last_error": (C.c_char_p, []),
+    "am_last_error_copy": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "am_abi_version": (C.c_int, []),
     "am_device_count": (C.c_int, []),
-    "am_automaton_build": (C.c_int, [C.POINTER(U8Slice), C.c_size_t, C.c_int, C.POINTER(LowerTable), C.POINTER(Options), C.POINTER(C.c_void_p)]),
+    "am_automaton_build": (C.c_int, [_P(U8Slice), C.c_size_t, _P(LowerTable), _P(Options), _P(C.c_void_p)]),
     "am_automaton_free": (None, [C.c_void_p]),
-    "am_debug_host_filter": (C.c_int, [C.c_void_p, U8Slice, C.c_uint32, C.c_void_p]),
-    "am_automaton_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
-    "am_contains_any": (C.c_int, [C.c_void_p, U8Slice, C.POINTER(C.c_int)]),
-    "am_count_matches": (C.c_int, [C.c_void_p, U8Slice, C.POINTER(C.c_uint64)]),
-    "am_find_all": (C.c_int, [C.c_void_p, U8Slice, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
-    "am_contains_all": (C.c_int, [C.c_void_p, U8Slice, C.POINTER(C.c_int)]),
-    "am_count_matches_dev": (C.c_int, [C.c_void_p, DevText, C.c_void_p, C.POINTER(C.c_uint64)]),
-    "am_contains_any_dev": (C.c_int, [C.c_void_p, DevText, C.c_void_p, C.POINTER(C.c_int)]),
-    "am_find_all_dev": (C.c_int, [C.c_void_p, DevText, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
-    "am_shard_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "am_replacer_build": (C.c_int, [C.POINTER(U8Slice), C.POINTER(U8Slice), C.c_size_t, C.c_int, C.POINTER(LowerTable), C.POINTER(Options), C.POINTER(C.c_void_p)]),
+    "am_automaton_prepare": (C.c_int, [C.c_void_p, C.c_int]),
+    "am_debug_host_filter": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), C.c_uint32, C.c_void_p]),
+    "am_automaton_info": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64), _P(C.c_int)]),
+    "am_contains_any": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), _P(C.c_int)]),
+    "am_count_matches": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), _P(C.c_uint64)]),
+    "am_find_all": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), C.c_void_p, C.c_size_t, _P(C.c_uint64)]),
+    "am_contains_all": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), _P(C.c_int)]),
+    "am_count_matches_dev": (C.c_int, [C.c_void_p, C.c_int, _P(DevText), C.c_void_p, _P(C.c_uint64)]),
+    "am_contains_any_dev": (C.c_int, [C.c_void_p, C.c_int, _P(DevText), C.c_void_p, _P(C.c_int)]),
+    "am_find_all_dev": (C.c_int, [C.c_void_p, C.c_int, _P(DevText), C.c_void_p, C.c_void_p, C.c_size_t, _P(C.c_uint64)]),
+    "am_shard_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64)]),
+    "am_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "am_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, _P(C.c_void_p)]),
+    "am_comm_free": (None, [C.c_void_p]),
+    "am_count_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(DevText), C.c_void_p, _P(ShardResult)]),
+    "am_find_all_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(DevText), C.c_void_p, C.c_void_p, C.c_size_t, _P(ShardResult)]),
+    "am_contains_any_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(DevText), C.c_void_p, _P(C.c_int)]),
+    "am_shard_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "am_comm_allreduce_u64": (C.c_int, [C.c_void_p, _P(C.c_uint64), C.c_int, C.c_void_p]),
+    "am_replacer_build": (C.c_int, [_P(U8Slice), _P(U8Slice), C.c_size_t, C.c_int, _P(LowerTable), _P(Options), _P(C.c_void_p)]),
+    "am_replacer_build_stored": (C.c_int, [_P(U8Slice), _P(C.c_uint32), _P(C.c_uint32), _P(U8Slice), C.c_size_t, C.c_int, _P(LowerTable), _P(Options), _P(C.c_void_p)]),
     "am_replacer_free": (None, [C.c_void_p]),
-    "am_replacer_run": (C.c_int, [C.c_void_p, U8Slice, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "am_replacer_run": (C.c_int, [C.c_void_p, C.c_int, _P(U8Slice), C.c_uint64, _P(C.c_void_p), _P(C.c_uint64), _P(C.c_int)]),
+    "am_replacer_run_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, _P(C.c_void_p), _P(C.c_uint64), _P(C.c_int)]),
     "am_replacer_last_passes": (C.c_uint64, []),
     "am_replacer_last_rescans": (C.c_uint64, []),
+    "am_replacer_last_profile": (C.c_int, [_P(C.c_float), _P(C.c_uint64)]),
     "am_free": (None, [C.c_void_p]),
-    "am_lower_utf8": (C.c_int, [C.POINTER(LowerTable), U8Slice, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]),
-    "am_skip_code_points_backwards": (C.c_int, [U8Slice, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
+    "am_dev_free": (None, [C.c_void_p]),
+    "am_lower_utf8": (C.c_int, [_P(LowerTable), _P(U8Slice), C.c_void_p, C.c_size_t, _P(C.c_uint64)]),
+    "am_skip_code_points_backwards": (C.c_int, [_P(U8Slice), C.c_int64, C.c_int64, _P(C.c_int64)]),
     "am_profile_enable": (C.c_int, [C.c_int]),
-    "am_profile_last_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),
+    "am_profile_last_scan_ms": (C.c_int, [_P(C.c_float)]),
     "am_profile_kernel_launches": (C.c_uint64, []),
     "am_synth_fill_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p, C.c_uint32, C.c_void_p]),
-    "am_synth_plant_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(U8Slice), C.c_size_t, C.c_uint32, C.c_void_p]),
+    "am_synth_plant_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _P(U8Slice), C.c_size_t, C.c_uint32, C.c_void_p]),
 }
 
 _lib = None

@@ -47,26 +47,39 @@ class _Needles:
 
 
 class AcMachine:
-    """`AcMachine v` (:108-123).  Immutable; the device image is shared by all calls."""
+    """`AcMachine v` (:108-123).  Immutable and case-agnostic like the reference's: `run_text` and `run_lower` run
+    the SAME machine (:539-553); the device image of a case mode is built when that mode is first used.
+    `case_sensitivity` is only the DEFAULT mode of the convenience methods below (and the image built eagerly)."""
 
     def __init__(self, needles_with_values: Sequence[Tuple[Any, Any]], case_sensitivity=CaseSensitivity.CaseSensitive,
                  lower_table: LowerTableArg | None = None, device: int = -1, force_kernel: int = 0):
         self.values = [v for _, v in needles_with_values]
         self._needles = _Needles([n for n, _ in needles_with_values])
         self.case_sensitivity = CaseSensitivity(case_sensitivity)
-        self._lower = (lower_table or default_lower_table()) if self.case_sensitivity == CaseSensitivity.IgnoreCase else None
+        self._lower = lower_table or default_lower_table()
         opts = _ffi.Options(device, force_kernel, (C.c_uint64 * 6)())
         h = C.c_void_p()
-        _ffi.check(_ffi.lib().am_automaton_build(self._needles.arr, len(self.values), int(self.case_sensitivity),
-                                                 self._lower.ptr() if self._lower else None, C.byref(opts), C.byref(h)))
+        _ffi.check(_ffi.lib().am_automaton_build(self._needles.arr, len(self.values), self._lower.ptr(), C.byref(opts), C.byref(h)))
         self.handle = h
         self._owner = True
+        try:
+            _ffi.check(_ffi.lib().am_automaton_prepare(h, int(self.case_sensitivity)))   # errors of the default mode surface here
+        except Exception:
+            self.__del__()
+            raise
 
     def with_values(self, values):
         """`fmap` on AcMachine (Functor, :123): same device image, remapped payloads."""
+        return self._share(values=list(values))
+
+    def with_case(self, case_sensitivity):
+        """The same machine with another default case mode (what `Searcher.setCaseSensitivity` needs: no rebuild)."""
+        return self._share(case_sensitivity=CaseSensitivity(case_sensitivity))
+
+    def _share(self, **changes):
         m = object.__new__(AcMachine)
         m.__dict__.update(self.__dict__)
-        m.values = list(values)
+        m.__dict__.update(changes)
         m._owner = False
         m._parent = self  # keeps the handle alive
         return m
@@ -80,70 +93,81 @@ class AcMachine:
                 pass
             self.handle = None
 
-    def info(self):
+    def _cs(self, case) -> int:
+        return int(self.case_sensitivity if case is None else CaseSensitivity(case))
+
+    def info(self, case=None):
         ns, mx, halo, kind = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
-        _ffi.check(_ffi.lib().am_automaton_info(self.handle, C.byref(ns), C.byref(mx), C.byref(halo), C.byref(kind)))
+        _ffi.check(_ffi.lib().am_automaton_info(self.handle, self._cs(case), C.byref(ns), C.byref(mx), C.byref(halo), C.byref(kind)))
         return {"num_states": ns.value, "max_needle_bytes": mx.value, "halo_bytes": halo.value, "kernel_kind": kind.value}
 
-    def host_filter_flags(self, text, align: int = 0) -> np.ndarray:
+    def host_filter_flags(self, text, align: int = 0, case=None) -> np.ndarray:
         """Introspection (works on a host image, device=-2): the fast path's q-gram filter evaluated on the host for every
         start position; bit 0 = shared-memory bitmap passes, bit 1 = second level passes (am_debug_host_filter)."""
         t = as_text(text)
         out = np.zeros(max(1, t.len), dtype=np.uint8)
-        _ffi.check(_ffi.lib().am_debug_host_filter(self.handle, t.slice(), align, out.ctypes.data))
+        sl = t.slice()
+        _ffi.check(_ffi.lib().am_debug_host_filter(self.handle, self._cs(case), C.byref(sl), align, out.ctypes.data))
         return out[: t.len]
 
     # ---- raw results (needle indices) -------------------------------------------------------------
-    def find_all(self, text) -> np.ndarray:
+    def find_all(self, text, case=None) -> np.ndarray:
         """All matches in the reference's callback order as a structured array (end_pos, needle_id)."""
         t = as_text(text)
-        cap = 4096
+        sl = t.slice()
+        cap = 4096 + t.len // 256
         while True:
             out = np.empty(cap, dtype=MATCH_DTYPE)
             n = C.c_uint64()
-            rc = _ffi.lib().am_find_all(self.handle, t.slice(), out.ctypes.data, cap, C.byref(n))
-            if rc == _ffi.AM_E_OVERFLOW:
+            rc = _ffi.lib().am_find_all(self.handle, self._cs(case), C.byref(sl), out.ctypes.data, cap, C.byref(n))
+            if rc == _ffi.AM_E_OVERFLOW:       # the call reports the capacity it needs: one retry
                 cap = int(n.value)
                 continue
             _ffi.check(rc)
             return out[: n.value]
 
-    def count_matches(self, text) -> int:
+    def count_matches(self, text, case=None) -> int:
         t = as_text(text)  # keep the buffer alive across the call
+        sl = t.slice()
         n = C.c_uint64()
-        _ffi.check(_ffi.lib().am_count_matches(self.handle, t.slice(), C.byref(n)))
+        _ffi.check(_ffi.lib().am_count_matches(self.handle, self._cs(case), C.byref(sl), C.byref(n)))
         return n.value
 
-    def contains_any(self, text) -> bool:
+    def contains_any(self, text, case=None) -> bool:
         t = as_text(text)
+        sl = t.slice()
         b = C.c_int()
-        _ffi.check(_ffi.lib().am_contains_any(self.handle, t.slice(), C.byref(b)))
+        _ffi.check(_ffi.lib().am_contains_any(self.handle, self._cs(case), C.byref(sl), C.byref(b)))
         return bool(b.value)
 
-    def contains_all(self, text) -> bool:
+    def contains_all(self, text, case=None) -> bool:
         t = as_text(text)
+        sl = t.slice()
         b = C.c_int()
-        _ffi.check(_ffi.lib().am_contains_all(self.handle, t.slice(), C.byref(b)))
+        _ffi.check(_ffi.lib().am_contains_all(self.handle, self._cs(case), C.byref(sl), C.byref(b)))
         return bool(b.value)
 
     # ---- device-resident variants (dev_ptr: CUDA device pointer as int) -----------------------------
     def _dev_text(self, dev_ptr, text_len, report_begin=0, pos_base=0):
         return _ffi.DevText(dev_ptr, text_len, report_begin, pos_base)
 
-    def count_matches_dev(self, dev_ptr, text_len, report_begin=0, pos_base=0, stream=None) -> int:
+    def count_matches_dev(self, dev_ptr, text_len, report_begin=0, pos_base=0, stream=None, case=None) -> int:
         n = C.c_uint64()
-        _ffi.check(_ffi.lib().am_count_matches_dev(self.handle, self._dev_text(dev_ptr, text_len, report_begin, pos_base), stream, C.byref(n)))
+        t = self._dev_text(dev_ptr, text_len, report_begin, pos_base)
+        _ffi.check(_ffi.lib().am_count_matches_dev(self.handle, self._cs(case), C.byref(t), stream, C.byref(n)))
         return n.value
 
-    def contains_any_dev(self, dev_ptr, text_len, report_begin=0, pos_base=0, stream=None) -> bool:
+    def contains_any_dev(self, dev_ptr, text_len, report_begin=0, pos_base=0, stream=None, case=None) -> bool:
         b = C.c_int()
-        _ffi.check(_ffi.lib().am_contains_any_dev(self.handle, self._dev_text(dev_ptr, text_len, report_begin, pos_base), stream, C.byref(b)))
+        t = self._dev_text(dev_ptr, text_len, report_begin, pos_base)
+        _ffi.check(_ffi.lib().am_contains_any_dev(self.handle, self._cs(case), C.byref(t), stream, C.byref(b)))
         return bool(b.value)
 
-    def find_all_dev(self, dev_ptr, text_len, out_dev_ptr, cap, report_begin=0, pos_base=0, stream=None) -> int:
+    def find_all_dev(self, dev_ptr, text_len, out_dev_ptr, cap, report_begin=0, pos_base=0, stream=None, case=None) -> int:
         """Sorted am_match records into device memory; returns n_found (raises AM_E_OVERFLOW if > cap)."""
         n = C.c_uint64()
-        rc = _ffi.lib().am_find_all_dev(self.handle, self._dev_text(dev_ptr, text_len, report_begin, pos_base), stream, out_dev_ptr, cap, C.byref(n))
+        t = self._dev_text(dev_ptr, text_len, report_begin, pos_base)
+        rc = _ffi.lib().am_find_all_dev(self.handle, self._cs(case), C.byref(t), stream, out_dev_ptr, cap, C.byref(n))
         if rc == _ffi.AM_E_OVERFLOW:
             raise OverflowError(n.value)
         _ffi.check(rc)
@@ -151,20 +175,18 @@ class AcMachine:
 
 
 def build(needles_with_values: Sequence[Tuple[Any, Any]], **kw) -> AcMachine:
-    """`build :: [(Text, v)] -> AcMachine v` (:176)."""
+    """`build :: [(Text, v)] -> AcMachine v` (:176).  One machine for both case modes."""
     return AcMachine(needles_with_values, **kw)
 
 
 def run_with_case(case_sensitivity, seed, f: Callable[[Any, Match], Any], machine: AcMachine, text):
     """`runWithCase` (:443): left fold of `f` over all matches; `f` returns Step(acc) or Done(acc).
 
-    The machine carries the case mode it was built for (the device image differs); asking for the
-    other mode rebuilds nothing and is an error, as the reference's wrappers never do that either.
+    Any machine runs in either mode, as in the reference (its own test helper builds once and picks the mode per
+    call, tests/Data/Text/AhoCorasickSpec.hs:252-261); for IgnoreCase the caller has lower-cased the needles (:543-546).
     """
-    if CaseSensitivity(case_sensitivity) != machine.case_sensitivity:
-        raise ValueError("machine was built for %s" % machine.case_sensitivity.name)
     acc = seed
-    ms = machine.find_all(text)
+    ms = machine.find_all(text, case=CaseSensitivity(case_sensitivity))
     values = machine.values
     for pos, nid in zip(ms["end_pos"].tolist(), ms["needle_id"].tolist()):
         nxt = f(acc, Match(pos, values[nid]))

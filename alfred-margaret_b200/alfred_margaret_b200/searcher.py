@@ -55,8 +55,11 @@ def case_sensitivity(s: Searcher) -> CaseSensitivity:
 
 
 def set_case_sensitivity(case_, s: Searcher) -> Searcher:
-    """`setCaseSensitivity` (:142-145): keeps the needles; the device image is rebuilt for the new mode."""
-    return Searcher(case_, s._needles, **s._kw)
+    """`setCaseSensitivity` (:142-145): flips the flag; needles and automaton are shared, nothing is rebuilt."""
+    out = Searcher.__new__(Searcher)
+    out._case, out._kw, out._needles = CaseSensitivity(case_), s._kw, s._needles
+    out._automaton = s._automaton.with_case(out._case)
+    return out
 
 
 def map_searcher(f, s: Searcher) -> Searcher:
@@ -70,12 +73,12 @@ def map_searcher(f, s: Searcher) -> Searcher:
 
 def contains_any(s: Searcher, text) -> bool:
     """`containsAny` (:156-164): the fold returns `Done True` on the first match == (count > 0)."""
-    return s._automaton.contains_any(text)
+    return s._automaton.contains_any(text, case=s._case)
 
 
 def contains_all(s: Searcher, text) -> bool:
     """`containsAll` (:173-187), for searchers from build_needle_id_searcher."""
-    return s._automaton.contains_all(text)
+    return s._automaton.contains_all(text, case=s._case)
 
 
 # ---- aeson-compatible JSON (`instance ToJSON / FromJSON (Searcher v)`, :68-77) -------------------------------------

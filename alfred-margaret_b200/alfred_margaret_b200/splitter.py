@@ -1,8 +1,8 @@
 """Host mirror of `Data.Text.AhoCorasick.Splitter` (src/Data/Text/AhoCorasick/Splitter.hs) -- SURVEY.md 8f rank 2.
 
 A single-needle automaton; splitting is the reference's fold (`stepAccum` :158-170, `finalizeAccum` :140-147)
-over the ordered match list the device returns.  The reference builds ONE machine and runs it in either case
-mode; here the device image depends on the mode, so a Splitter lazily holds one machine per mode.
+over the ordered match list the device returns.  Like the reference (:63-67) a Splitter holds ONE machine and runs
+it in either case mode.
 """
 from __future__ import annotations
 
@@ -17,13 +17,10 @@ class Splitter:
     def __init__(self, separator, **kw):
         self._sep = separator.encode("utf-8") if isinstance(separator, str) else bytes(separator)
         self._kw = kw
-        self._machines = {}
+        self._machine = AcMachine([(self._sep, ())], **kw)
 
-    def machine(self, cs) -> AcMachine:
-        cs = CaseSensitivity(cs)
-        if cs not in self._machines:
-            self._machines[cs] = AcMachine([(self._sep, ())], case_sensitivity=cs, **self._kw)
-        return self._machines[cs]
+    def machine(self, cs=CaseSensitivity.CaseSensitive) -> AcMachine:
+        return self._machine
 
     def __eq__(self, other):                       # instance Eq Splitter (:175-177)
         return isinstance(other, Splitter) and self._sep == other._sep
@@ -48,7 +45,7 @@ def automaton(s: Splitter) -> AcMachine:
 def _split_reverse(s: Splitter, text, ignore_case: bool) -> List[bytes]:
     t = as_text(text)
     hay = t.tobytes()
-    ends = s.machine(CaseSensitivity.IgnoreCase if ignore_case else CaseSensitivity.CaseSensitive).find_all(t)["end_pos"].tolist()
+    ends = s.machine().find_all(t, case=CaseSensitivity.IgnoreCase if ignore_case else CaseSensitivity.CaseSensitive)["end_pos"].tolist()
     res, fragment_start = [], 0                    # zeroAccum (:150-152)
     if ignore_case:
         sep_len = sum((b & 0xC0) != 0x80 for b in s._sep)        # Text.length (separator s): code points (:113)
@@ -61,9 +58,11 @@ def _split_reverse(s: Splitter, text, ignore_case: bool) -> List[bytes]:
             sep_start = new_fragment_start - sep_len
         if sep_start < fragment_start:             # overlaps the previous separator: ignored (:163-164)
             continue
-        res.insert(0, hay[fragment_start:sep_start])
+        res.append(hay[fragment_start:sep_start])  # the reference conses (:165); appended here, reversed once below
         fragment_start = new_fragment_start
-    return [hay[fragment_start:]] + res            # finalizeAccum (:140-147)
+    res.append(hay[fragment_start:])               # finalizeAccum (:140-147)
+    res.reverse()
+    return res
 
 
 def split_reverse(s: Splitter, text) -> List[bytes]:

@@ -97,7 +97,8 @@ def lower_utf8(text, table: LowerTableArg | None = None) -> bytes:
     cap = 4 * t.len + 8
     out = (C.c_uint8 * cap)()
     n = C.c_uint64()
-    _ffi.check(_ffi.lib().am_lower_utf8(table.ptr(), t.slice(), out, cap, C.byref(n)))
+    sl = t.slice()
+    _ffi.check(_ffi.lib().am_lower_utf8(table.ptr(), C.byref(sl), out, cap, C.byref(n)))
     return bytes(out[: n.value])
 
 
@@ -105,7 +106,8 @@ def skip_code_points_backwards(text, index: int, n: int) -> int:
     """`skipCodePointsBackwards` (:256-276); raises where the reference calls `error`."""
     t = as_text(text)
     out = C.c_int64()
-    rc = _ffi.lib().am_skip_code_points_backwards(t.slice(), index, n, C.byref(out))
+    sl = t.slice()
+    rc = _ffi.lib().am_skip_code_points_backwards(C.byref(sl), index, n, C.byref(out))
     if rc == _ffi.AM_E_BADARG:
         raise ValueError("Invalid use of skipCodePointsBackwards")
     _ffi.check(rc)

@@ -20,10 +20,14 @@ namespace am {
 
 thread_local std::string g_last_error;
 thread_local uint64_t g_last_passes = 0, g_last_rescans = 0;
+thread_local float g_last_replacer_ms = 0.f;
+thread_local uint64_t g_last_replacer_bytes = 0;
 std::atomic<uint64_t> g_kernel_launches{0};
 static std::atomic<int> g_profile{0};
+// profiling: the event pair (owned by a pooled workspace) around the scan kernels of this thread's most recent scan
 thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-thread_local bool g_ev_valid = false;
+thread_local int g_ev_device = -1;
+bool profiling_enabled() { return g_profile.load(std::memory_order_relaxed) != 0; }
 
 int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -44,7 +48,7 @@ static int usable_device_count() {
 
 // ---- device memory helpers ---------------------------------------------------------------------------
 template <class T>
-static int upload(am_automaton* a, const std::vector<T>& v, const T** out) {
+static int upload(Image* a, const std::vector<T>& v, const T** out) {
   void* p = nullptr;
   size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
   cudaError_t e = cudaMalloc(&p, bytes);
@@ -59,8 +63,10 @@ static int upload(am_automaton* a, const std::vector<T>& v, const T** out) {
 }
 
 Workspace::~Workspace() {
-  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases})
+  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases, (void*)seen_bits})
     if (p) cudaFree(p);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
   if (h_scalars) cudaFreeHost(h_scalars);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (scan_stream) cudaStreamDestroy(scan_stream);
@@ -97,35 +103,46 @@ int Workspace::need_segs(uint64_t n) {
   return ws_grow((void**)&seg_bases, &seg_bases_bytes, n * 8 + 16, "segment bases");
 }
 
-Workspace* acquire_ws(const am_automaton* ca) {
-  am_automaton* a = const_cast<am_automaton*>(ca);
+int Workspace::need_seen(uint64_t bits) { return ws_grow((void**)&seen_bits, &seen_bytes, (bits + 31) / 32 * 4 + 16, "needle bit set"); }
+
+Image::~Image() {
+  DeviceGuard g;
+  if (device >= 0) g.enter(device);
+  for (Workspace* w : ws_pool) delete w;
+  for (void* p : dev_allocs) cudaFree(p);
+}
+
+constexpr size_t SCALARS_BYTES = 1024;   // d_scalars / h_scalars: [0..64) scan counters, [64..) the gathered per-rank counts of the sharded calls
+
+Workspace* acquire_ws(const Image* ca) {
+  Image* a = const_cast<Image*>(ca);
   {
     std::lock_guard<std::mutex> g(a->ws_mutex);
     if (!a->ws_pool.empty()) { Workspace* w = a->ws_pool.back(); a->ws_pool.pop_back(); return w; }
   }
   Workspace* w = new Workspace();
-  if (cudaMalloc((void**)&w->d_scalars, 256) != cudaSuccess || cudaMallocHost((void**)&w->h_scalars, 256) != cudaSuccess) {
+  if (cudaMalloc((void**)&w->d_scalars, SCALARS_BYTES) != cudaSuccess || cudaMallocHost((void**)&w->h_scalars, SCALARS_BYTES) != cudaSuccess) {
     cudaGetLastError(); delete w; return nullptr;
   }
   return w;
 }
-void release_ws(const am_automaton* ca, Workspace* w) {
-  am_automaton* a = const_cast<am_automaton*>(ca);
+void release_ws(const Image* ca, Workspace* w) {
+  Image* a = const_cast<Image*>(ca);
   std::lock_guard<std::mutex> g(a->ws_mutex);
   a->ws_pool.push_back(w);
 }
 
-int check_ready(const am_automaton* a) {
+int check_ready(const Image* a, DeviceGuard* g) {
   if (!a) return fail(AM_E_BADARG, "automaton is null");
   if (a->device < 0) return fail(AM_E_NODEVICE, "automaton was built without a device (host image only); there is no CPU fallback");
-  cudaError_t e = cudaSetDevice(a->device);
+  cudaError_t e = g->enter(a->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   return AM_OK;
 }
 
 
 // Launch one scan in `mode`; COUNT/EMIT totals land in ws->d_scalars[0], the ANY flag in d_scalars[8..].
-int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st) {
+int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st) {
   if (t.report_begin > t.text_len) return fail(AM_E_BADARG, "report_begin > text_len");
   if (t.text_len > 0 && !t.dev_text) return fail(AM_E_BADARG, "dev_text is null");
   if (bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits > 64) return fail(AM_E_UNSUPPORTED, "position and needle rank do not fit a 64-bit sort key");
@@ -156,11 +173,13 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
     sa.seg_counts = ws->seg_counts; sa.seg_cap = seg_cap; sa.ovf_base = ws->ovf_base; sa.ovf_cap = ws->ovf_cap;
     ws->emit_segmented = true;   // (cleared again below if the scan has to take the walk kernel)
   }
-  const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+  const bool prof = profiling_enabled();
   if (prof) {
-    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    if (!ws->ev0) { cudaEventCreate(&ws->ev0); cudaEventCreate(&ws->ev1); }
+    g_ev0 = ws->ev0; g_ev1 = ws->ev1; g_ev_device = a->device;
     cudaEventRecord(g_ev0, st);
   }
+  ws->last_kernel = a->kernel_kind;
   if (a->kernel_kind == 2 && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
     // runLower on the filter kernel: scan a lowered copy of the text (same byte offsets).  Code points whose
     // lowering changes their UTF-8 length stay as they are in the copy and are matched by the needle variants
@@ -182,7 +201,7 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) return cuda_fail(e, "one-pass IgnoreCase scan");
       if (*reinterpret_cast<int*>(ws->h_scalars + 24) == 0) {
-        if (prof) { cudaEventRecord(g_ev1, st); g_ev_valid = true; }
+        if (prof) cudaEventRecord(g_ev1, st);
         return AM_OK;
       }
       sa.lower_ascii = 0; sa.d_nonascii = nullptr;             // not ASCII: start over
@@ -207,19 +226,19 @@ int launch_scan(const am_automaton* a, Workspace* ws, const am_dev_text& t, int 
       sa.text = ws->aux_a + a0;
       e = launch_filter(a->dev, sa, mode, st);
     } else {
-      ws->emit_segmented = false;
+      ws->emit_segmented = false; ws->last_kernel = 1;
       e = launch_walk(a->dev, sa, mode, st);
     }
   } else {
     e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
   }
-  if (prof) { cudaEventRecord(g_ev1, st); g_ev_valid = true; }
+  if (prof) cudaEventRecord(g_ev1, st);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return AM_OK;
 }
 
-static int read_scalars(Workspace* ws, cudaStream_t st) {
-  cudaError_t e = cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, 16, cudaMemcpyDeviceToHost, st);
+int read_scalars(Workspace* ws, cudaStream_t st, size_t bytes) {
+  cudaError_t e = cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, bytes, cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scalars)");
   e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return cuda_fail(e, "scan kernel");
@@ -231,29 +250,38 @@ static int read_scalars(Workspace* ws, cudaStream_t st) {
 //    puts every key into its final place.  If some segment overflowed, segments + overflow area are compacted and
 //    radix-sorted instead; if even the overflow area was too small the buffers grow and the scan runs again.
 //  * walk kernel: global append + radix sort.
-int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked) {
-  if (unpacked) *unpacked = false;
-  uint64_t span = t.text_len - std::min(t.report_begin, t.text_len);
-  int rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
+// Two phases, so that a caller can queue more work (the sharded calls: the all-gather of the counts) before the one host
+// round trip:
+//   emit_enqueue  launches the scan and -- for segmented emission -- the segment scan and the segment sort; afterwards
+//                 d_scalars[0..8) = keys produced (global append) or keys that overflowed their segment (segmented) and
+//                 d_scalars[8..16) = keys stored in the segments (segmented); their sum is the match count either way
+//   emit_finish   reads the counters and handles the slow paths (overflow: compaction + radix sort; buffers too small: rescan)
+int emit_enqueue(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, am_match* matches, uint64_t matches_cap) {
+  int rc = launch_scan(a, ws, t, MODE_EMIT, st);
   if (rc) return rc;
+  if (ws->emit_segmented) {
+    const size_t stb = seg_scan_temp_bytes(ws->num_segs);
+    if ((rc = ws->need_sort_temp(stb))) return rc;
+    cudaError_t e = launch_seg_scan(ws->sort_temp, stb, ws->seg_counts, ws->num_segs, ws->seg_cap, ws->seg_bases, st);
+    if (e == cudaSuccess)   // d_scalars[8..16): number of keys stored in the segments
+      e = cudaMemcpyAsync(ws->d_scalars + 8, ws->seg_bases + ws->num_segs, 8, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "segment scan");
+    // queued before the host knows whether a segment overflowed (the common case: none did, and then this was the last
+    // kernel of the call -- one host round trip in total); after an overflow its output is simply overwritten
+    e = launch_seg_sort(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_b, matches, matches_cap, a->host.rank_bits, a->dev.id_of_rank, st);
+    if (e != cudaSuccess) return cuda_fail(e, "segment sort");
+  }
+  return AM_OK;
+}
+
+// The host has synchronised `st` and ws->h_scalars holds the counters of emit_enqueue.
+int emit_finish(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked) {
+  if (unpacked) *unpacked = false;
   const int end_bit = std::min(64, bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits);
+  int rc;
   for (int attempt = 0;; attempt++) {
-    rc = launch_scan(a, ws, t, MODE_EMIT, st);
-    if (rc) return rc;
     const uint64_t cap = ws->keys_a_bytes / 8;
     if (ws->emit_segmented) {
-      const size_t stb = seg_scan_temp_bytes(ws->num_segs);
-      if ((rc = ws->need_sort_temp(stb))) return rc;
-      cudaError_t e = launch_seg_scan(ws->sort_temp, stb, ws->seg_counts, ws->num_segs, ws->seg_cap, ws->seg_bases, st);
-      if (e == cudaSuccess)   // d_scalars[8..16): number of keys stored in the segments
-        e = cudaMemcpyAsync(ws->d_scalars + 8, ws->seg_bases + ws->num_segs, 8, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return cuda_fail(e, "segment scan");
-      // queued before the host knows whether a segment overflowed (the common case: none did, and then this was the last
-      // kernel of the call -- one host round trip in total); after an overflow its output is simply overwritten below
-      e = launch_seg_sort(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_b, matches, matches_cap, a->host.rank_bits, a->dev.id_of_rank, st);
-      if (e != cudaSuccess) return cuda_fail(e, "segment sort");
-      rc = read_scalars(ws, st);
-      if (rc) return rc;
       const uint64_t n_ovf = *reinterpret_cast<uint64_t*>(ws->h_scalars), stored = *reinterpret_cast<uint64_t*>(ws->h_scalars + 8);
       *n = stored + n_ovf;
       if (n_ovf == 0) {
@@ -261,7 +289,7 @@ int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, 
         return AM_OK;
       }
       if (n_ovf <= ws->ovf_cap && *n <= ws->keys_b_bytes / 8) {
-        e = launch_seg_compact(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_a + ws->ovf_base, n_ovf, stored, ws->keys_b, st);
+        cudaError_t e = launch_seg_compact(ws->keys_a, ws->seg_counts, ws->seg_bases, ws->num_segs, ws->seg_cap, ws->keys_a + ws->ovf_base, n_ovf, stored, ws->keys_b, st);
         if (e != cudaSuccess) return cuda_fail(e, "segment compaction");
         size_t tb = sort_temp_bytes(*n, end_bit);
         if ((rc = ws->need_sort_temp(tb))) return rc;
@@ -272,24 +300,32 @@ int find_all_sorted(const am_automaton* a, Workspace* ws, const am_dev_text& t, 
       }
       if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
       rc = ws->need_keys(2 * *n + 1024);   // half of the buffer is the overflow area: now it holds every key
-      if (rc) return rc;
-      continue;
+    } else {
+      *n = *reinterpret_cast<uint64_t*>(ws->h_scalars);
+      if (*n <= cap) {
+        if (*n == 0) return AM_OK;
+        size_t tb = sort_temp_bytes(*n, end_bit);
+        if ((rc = ws->need_sort_temp(tb))) return rc;
+        cudaError_t e = sort_keys(ws->sort_temp, tb, ws->keys_a, ws->keys_b, *n, end_bit, st);
+        if (e != cudaSuccess) return cuda_fail(e, "radix sort");
+        return AM_OK;
+      }
+      if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
+      rc = ws->need_keys(*n);              // exact size is now known: rescan
     }
-    rc = read_scalars(ws, st);
     if (rc) return rc;
-    *n = *reinterpret_cast<uint64_t*>(ws->h_scalars);
-    if (*n <= cap) break;
-    if (attempt >= 2) return fail(AM_E_INTERNAL, "match count kept growing");
-    rc = ws->need_keys(*n);  // exact size is now known: rescan
-    if (rc) return rc;
+    if ((rc = emit_enqueue(a, ws, t, st, matches, matches_cap))) return rc;
+    if ((rc = read_scalars(ws, st))) return rc;
   }
-  if (*n == 0) return AM_OK;
-  size_t tb = sort_temp_bytes(*n, end_bit);
-  rc = ws->need_sort_temp(tb);
+}
+
+int find_all_sorted(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked) {
+  const uint64_t span = t.text_len - std::min(t.report_begin, t.text_len);
+  int rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
   if (rc) return rc;
-  cudaError_t e = sort_keys(ws->sort_temp, tb, ws->keys_a, ws->keys_b, *n, end_bit, st);
-  if (e != cudaSuccess) return cuda_fail(e, "radix sort");
-  return AM_OK;
+  if ((rc = emit_enqueue(a, ws, t, st, matches, matches_cap))) return rc;
+  if ((rc = read_scalars(ws, st))) return rc;
+  return emit_finish(a, ws, t, st, n, matches, matches_cap, unpacked);
 }
 
 // ---- L1 text substrate helpers (host) -----------------------------------------------------------------------------
@@ -324,99 +360,8 @@ int lower_utf8_host(const LowerTable& lt, const uint8_t* in, int64_t len, std::v
 }
 
 
-}  // namespace am
-
-using namespace am;
-
-// =====================================================================================================
-// C ABI
-// =====================================================================================================
-extern "C" {
-
-const char* am_last_error(void) { return g_last_error.c_str(); }
-int am_abi_version(void) { return AM_ABI_VERSION; }
-int am_device_count(void) { return usable_device_count(); }
-
-int am_automaton_build(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower, const am_options* opts,
-                       am_automaton** out) {
-  if (!out) return fail(AM_E_BADARG, "out is null");
-  *out = nullptr;
-  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table (it may be empty)");
-  am_automaton* a = new am_automaton();
-  std::string err;
-  int rc = build_host_automaton(needles, n, cs, lower, &a->host, &err);
-  if (rc != AM_OK) { delete a; return fail(rc, err); }
-  const int want_dev = opts ? opts->device : -1;
-  const int force = opts ? opts->force_kernel : 0;
-  HostAutomaton& H = a->host;
-  // The q-gram filter keeps 16 private 64 Ki-bit copies of its bitmap in shared memory; beyond a few
-  // thousand distinct q-grams its false-positive rate (keys / 65 536) swamps the second level, and the
-  // per-segment walk is the better kernel.  force_kernel = 2 overrides the heuristic.
-  const bool filter_ok = H.q > 0;   // IgnoreCase runs the filter on a lowered copy of the text (launch_scan)
-  const bool filter_good = filter_ok && H.filter_keys <= 65536;   // measured (r1d): 20 k needles 1043 GB/s (filter) vs 309 (walk), 40 k 559 vs 234, 100 k 142 vs 212
-  a->kernel_kind = (force == 2 && filter_ok) || (force != 1 && filter_good) ? 2 : 1;
-  if (force == 2 && a->kernel_kind != 2) { delete a; return fail(AM_E_UNSUPPORTED, "filter kernel not applicable to this needle set"); }
-  if (want_dev == -2) { a->device = -1; *out = a; return AM_OK; }  // host image only (tests / introspection)
-
-  if (usable_device_count() == 0) { delete a; return fail(AM_E_NODEVICE, "no sm_100 CUDA device; libam_b200 has no CPU fallback"); }
-  int dev = want_dev;
-  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
-  cudaError_t e = cudaSetDevice(dev);
-  if (e != cudaSuccess) { delete a; return cuda_fail(e, "cudaSetDevice"); }
-  a->device = dev;
-
-  DevAutomaton& D = a->dev;
-  std::memset(&D, 0, sizeof D);
-  if (H.filter.empty()) { H.filter.assign(FILTER_WORDS, 0); }
-  if (H.filter2.empty()) { H.filter2.assign(T2_WORDS, 0); }
-  if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE, 0, 0}); H.jump_mask = 15; }
-  if (H.tails.empty()) H.tails.assign(4, 0);
-  if ((rc = upload(a, H.dense, &D.dense)) || (rc = upload(a, H.fail, &D.fail)) || (rc = upload(a, H.edges, &D.edges)) ||
-      (rc = upload(a, H.jump, &D.jump)) || (rc = upload(a, H.tails, &D.tails)) || (rc = upload(a, H.filter, &D.filter)) || (rc = upload(a, H.filter2, &D.filter2)) ||
-      (rc = upload(a, H.own_off, &D.own_off)) || (rc = upload(a, H.own_rank, &D.own_rank)) ||
-      (rc = upload(a, H.first_out, &D.first_out)) || (rc = upload(a, H.next_out, &D.next_out)) ||
-      (rc = upload(a, H.chain_count, &D.chain_count)) || (rc = upload(a, H.id_of_rank, &D.id_of_rank)) ||
-      (rc = upload(a, H.len_of_rank, &D.len_of_rank)) || (rc = upload(a, H.lower.stage1, &D.lower1)) ||
-      (rc = upload(a, H.lower.stage2, &D.lower2)) || (rc = upload(a, H.cdfa, &D.cdfa)) ||
-      (rc = upload(a, std::vector<uint8_t>(H.cls, H.cls + 256), &D.cls))) {
-    am_automaton_free(a);
-    return rc;
-  }
-  D.dense_states = H.dense_states; D.edge_mask = H.edge_mask; D.jump_mask = H.jump_mask;
-  D.q = H.q; D.qmask = qgram_mask(H.q); D.min_len = H.min_len; D.max_len = H.max_len; D.rank_bits = H.rank_bits;
-  D.num_states = H.num_states; D.num_needles = H.num_needles;
-  D.ignore_case = cs == AM_IGNORE_CASE; D.halo = (uint32_t)H.halo_bytes;
-  D.t2_exact = H.t2_exact; D.t2_empty_key = H.t2_empty_key;
-  D.cdfa_states = H.cdfa_states; D.cdfa_shift = H.cdfa_shift;
-  *out = a;
-  return AM_OK;
-}
-
-void am_automaton_free(am_automaton* a) {
-  if (!a) return;
-  if (a->device >= 0) cudaSetDevice(a->device);
-  for (Workspace* w : a->ws_pool) delete w;
-  for (void* p : a->dev_allocs) cudaFree(p);
-  delete a;
-}
-
-int am_automaton_info(const am_automaton* a, uint64_t* num_states, uint64_t* max_needle_bytes, uint64_t* halo_bytes, int* kernel_kind) {
-  if (!a) return fail(AM_E_BADARG, "automaton is null");
-  if (num_states) *num_states = a->host.num_states;
-  if (max_needle_bytes) *max_needle_bytes = a->host.max_len;
-  if (halo_bytes) *halo_bytes = a->host.halo_bytes;
-  if (kernel_kind) *kernel_kind = a->kernel_kind;
-  return AM_OK;
-}
-
 // Host model of filter_kernel's two filter levels (am_filter.cu: fk_probe16 / fk_probe16_s2, fk_phase_a) on the host image.
-int am_debug_host_filter(const am_automaton* a, am_u8slice text, uint32_t align, uint8_t* out_flags) {
-  if (!a || !out_flags) return fail(AM_E_BADARG, "null argument");
-  if (text.len < 0 || text.off < 0 || (text.len > 0 && !text.ptr)) return fail(AM_E_BADARG, "bad text slice");
-  const HostAutomaton& H = a->host;
-  if (H.q == 0 || H.filter.empty()) return fail(AM_E_UNSUPPORTED, "this automaton has no q-gram filter");
-  const uint8_t* d = text.ptr + text.off;
-  const uint64_t n = (uint64_t)text.len;
+void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uint32_t align, uint8_t* out_flags) {
   auto byte_at = [&](uint64_t i) -> uint32_t { return i < n ? d[i] : 0u; };   // the kernel sees arbitrary bytes beyond the text: any value may only ADD candidates
   auto gram4 = [&](uint64_t i) -> uint32_t { return byte_at(i) | byte_at(i + 1) << 8 | byte_at(i + 2) << 16 | byte_at(i + 3) << 24; };
   const bool exact = H.t2_exact != 0;
@@ -462,63 +407,316 @@ int am_debug_host_filter(const am_automaton* a, am_u8slice text, uint32_t align,
     }
     out_flags[i] = (uint8_t)(level1 | (level2 << 1));
   }
+}
+
+
+}  // namespace am
+
+using namespace am;
+
+// =====================================================================================================
+// handle -> image of one case mode
+// =====================================================================================================
+namespace am {
+
+// Build the host image of `cs`, pick its kernel and upload it to the handle's device.
+static int build_image(const am_automaton* a, int cs, Image** out) {
+  Image* im = new Image();
+  const size_t n = a->needle_off.size() - 1;
+  std::vector<am_u8slice> slices(n);
+  for (size_t i = 0; i < n; i++) slices[i] = am_u8slice{a->needle_pool.data(), (int64_t)a->needle_off[i], (int64_t)(a->needle_off[i + 1] - a->needle_off[i])};
+  am_lower_table lt{a->lower_pairs.data(), a->lower_pairs.size()};
+  std::string err;
+  int rc = build_host_automaton(slices.data(), n, cs, cs == AM_IGNORE_CASE ? &lt : nullptr, &im->host, &err);
+  if (rc != AM_OK) { delete im; return fail(rc, err); }
+  HostAutomaton& H = im->host;
+  // The q-gram filter keeps its bitmaps in shared memory; beyond ~64 k distinct q-grams of the shortest form (q = 4) they
+  // saturate and the per-segment walk is the better kernel.  Longer q-grams (needle sets whose shortest needle has >= 6
+  // bytes) keep the filter selective far beyond that.  force_kernel overrides the heuristic.
+  const int force = a->force_kernel;
+  const bool filter_ok = H.q > 0;
+  const bool filter_good = filter_ok && (H.q > 4 || H.filter_keys <= 65536);
+  im->kernel_kind = (force == 2 && filter_ok) || (force != 1 && filter_good) ? 2 : 1;
+  if (force == 2 && im->kernel_kind != 2) { delete im; return fail(AM_E_UNSUPPORTED, "filter kernel not applicable to this needle set"); }
+  if (a->device < 0) { im->device = -1; *out = im; return AM_OK; }   // host image only (tests / introspection)
+
+  DeviceGuard g;
+  cudaError_t e = g.enter(a->device);
+  if (e != cudaSuccess) { delete im; return cuda_fail(e, "cudaSetDevice"); }
+  im->device = a->device;
+  DevAutomaton& D = im->dev;
+  std::memset(&D, 0, sizeof D);
+  if (H.filter.empty()) { H.filter.assign(FILTER_WORDS, 0); }
+  if (H.filter2.empty()) { H.filter2.assign(T2_WORDS, 0); }
+  if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE, 0, 0}); H.jump_mask = 15; }
+  if (H.tails.empty()) H.tails.assign(4, 0);
+  if ((rc = upload(im, H.dense, &D.dense)) || (rc = upload(im, H.fail, &D.fail)) || (rc = upload(im, H.edges, &D.edges)) ||
+      (rc = upload(im, H.jump, &D.jump)) || (rc = upload(im, H.tails, &D.tails)) || (rc = upload(im, H.filter, &D.filter)) || (rc = upload(im, H.filter2, &D.filter2)) ||
+      (rc = upload(im, H.own_off, &D.own_off)) || (rc = upload(im, H.own_rank, &D.own_rank)) ||
+      (rc = upload(im, H.first_out, &D.first_out)) || (rc = upload(im, H.next_out, &D.next_out)) ||
+      (rc = upload(im, H.chain_count, &D.chain_count)) || (rc = upload(im, H.id_of_rank, &D.id_of_rank)) ||
+      (rc = upload(im, H.len_of_rank, &D.len_of_rank)) || (rc = upload(im, H.lower.stage1, &D.lower1)) ||
+      (rc = upload(im, H.lower.stage2, &D.lower2)) || (rc = upload(im, H.cdfa, &D.cdfa)) ||
+      (rc = upload(im, std::vector<uint8_t>(H.cls, H.cls + 256), &D.cls))) {
+    delete im;
+    return rc;
+  }
+  D.dense_states = H.dense_states; D.edge_mask = H.edge_mask; D.jump_mask = H.jump_mask;
+  D.q = H.q; D.qmask = qgram_mask(H.q); D.min_len = H.min_len; D.max_len = H.max_len; D.rank_bits = H.rank_bits;
+  D.num_states = H.num_states; D.num_needles = H.num_needles;
+  D.ignore_case = cs == AM_IGNORE_CASE; D.halo = (uint32_t)H.halo_bytes;
+  D.t2_exact = H.t2_exact; D.t2_empty_key = H.t2_empty_key;
+  D.cdfa_states = H.cdfa_states; D.cdfa_shift = H.cdfa_shift;
+  *out = im;
+  return AM_OK;
+}
+
+int get_image(const am_automaton* ca, int cs, Image** out) {
+  if (!ca) return fail(AM_E_BADARG, "automaton is null");
+  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) return fail(AM_E_BADARG, "unknown case sensitivity");
+  am_automaton* a = const_cast<am_automaton*>(ca);
+  std::lock_guard<std::mutex> g(a->mu);
+  if (!a->img[cs]) {
+    if (cs == AM_IGNORE_CASE && !a->has_lower)
+      return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table (it may be empty): pass it to am_automaton_build");
+    Image* im = nullptr;
+    int rc = build_image(a, cs, &im);
+    if (rc) return rc;
+    a->img[cs] = im;
+  }
+  *out = a->img[cs];
+  return AM_OK;
+}
+
+}  // namespace am
+
+// Every compute entry point starts with this: image of the case mode, on its device (restored when `g` dies).
+#define AM_ENTER(a, cs)                                   \
+  Image* im = nullptr;                                    \
+  DeviceGuard guard;                                      \
+  { int rc_ = get_image((a), (cs), &im); if (rc_) return rc_; rc_ = check_ready(im, &guard); if (rc_) return rc_; }
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* am_last_error(void) { return g_last_error.c_str(); }
+size_t am_last_error_copy(char* buf, size_t cap) {
+  const size_t n = g_last_error.size();
+  if (buf && cap) { const size_t k = std::min(n, cap - 1); std::memcpy(buf, g_last_error.data(), k); buf[k] = 0; }
+  return n;
+}
+int am_abi_version(void) { return AM_ABI_VERSION; }
+int am_device_count(void) { return usable_device_count(); }
+
+int am_automaton_build(const am_u8slice* needles, size_t n, const am_lower_table* lower, const am_options* opts, am_automaton** out) {
+  if (!out) return fail(AM_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n > 0 && !needles) return fail(AM_E_BADARG, "needles is null");
+  if (n >= (1ull << 31)) return fail(AM_E_BADARG, "too many needles");
+  if (lower && lower->n > 0 && !lower->pairs) return fail(AM_E_BADARG, "bad lower table");
+  const int want_dev = opts ? opts->device : -1;
+  const int force = opts ? opts->force_kernel : 0;
+  if (force < 0 || force > 2) return fail(AM_E_BADARG, "unknown force_kernel");
+  am_automaton* a = new am_automaton();
+  a->force_kernel = force;
+  a->needle_off.assign(n + 1, 0);
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (needles[i].len < 0 || needles[i].off < 0 || (needles[i].len > 0 && !needles[i].ptr)) { delete a; return fail(AM_E_BADARG, "bad needle slice"); }
+    if ((uint64_t)needles[i].len >= (1ull << 24)) { delete a; return fail(AM_E_BADARG, "needle longer than 16 MiB"); }
+    total += (uint64_t)needles[i].len;
+    a->needle_off[i + 1] = total;
+  }
+  a->needle_pool.resize(total + 1);
+  for (size_t i = 0; i < n; i++)
+    if (needles[i].len) std::memcpy(a->needle_pool.data() + a->needle_off[i], needles[i].ptr + needles[i].off, (size_t)needles[i].len);
+  if (lower) {
+    a->has_lower = true;
+    for (size_t i = 0; i < lower->n; i++) {
+      if (lower->pairs[i].from_cp >= 0x110000 || lower->pairs[i].to_cp >= 0x110000) { delete a; return fail(AM_E_BADARG, "bad lower table"); }
+      a->lower_pairs.push_back(lower->pairs[i]);
+    }
+  }
+  if (want_dev == -2) { a->device = -1; *out = a; return AM_OK; }   // host images only (tests / introspection)
+  if (usable_device_count() == 0) { delete a; return fail(AM_E_NODEVICE, "no sm_100 CUDA device; libam_b200 has no CPU fallback"); }
+  int dev = want_dev;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+    cudaGetLastError(); delete a;
+    return fail(AM_E_NODEVICE, "device " + std::to_string(dev) + " is not an sm_100 device");
+  }
+  a->device = dev;
+  *out = a;
+  return AM_OK;
+}
+
+void am_automaton_free(am_automaton* a) { delete a; }
+
+int am_automaton_prepare(const am_automaton* a, int cs) {
+  Image* im = nullptr;
+  return get_image(a, cs, &im);
+}
+
+int am_automaton_info(const am_automaton* a, int cs, uint64_t* num_states, uint64_t* max_needle_bytes, uint64_t* halo_bytes, int* kernel_kind) {
+  Image* im = nullptr;
+  int rc = get_image(a, cs, &im);
+  if (rc) return rc;
+  if (num_states) *num_states = im->host.num_states;
+  if (max_needle_bytes) *max_needle_bytes = im->host.max_len;
+  if (halo_bytes) *halo_bytes = im->host.halo_bytes;
+  if (kernel_kind) *kernel_kind = im->kernel_kind;
+  return AM_OK;
+}
+
+static int check_slice(const am_u8slice* s) {
+  if (!s) return fail(AM_E_BADARG, "text slice is null");
+  if (s->len < 0 || s->off < 0 || (s->len > 0 && !s->ptr)) return fail(AM_E_BADARG, "bad text slice");
+  return AM_OK;
+}
+static int check_dev_text(const am_dev_text* t) {
+  if (!t) return fail(AM_E_BADARG, "device text is null");
+  return AM_OK;
+}
+
+// Host model of filter_kernel's two filter levels on the host image (am_filter_model.h: the very functions the kernel uses).
+int am_debug_host_filter(const am_automaton* a, int cs, const am_u8slice* text, uint32_t align, uint8_t* out_flags) {
+  int rc = check_slice(text); if (rc) return rc;
+  if (!out_flags) return fail(AM_E_BADARG, "null argument");
+  Image* im = nullptr;
+  if ((rc = get_image(a, cs, &im))) return rc;
+  const HostAutomaton& H = im->host;
+  if (H.q == 0 || H.filter.empty()) return fail(AM_E_UNSUPPORTED, "this automaton has no q-gram filter");
+  host_filter_model(H, text->ptr + text->off, (uint64_t)text->len, align, out_flags);
   return AM_OK;
 }
 
 // ---- device-resident entry points -------------------------------------------------------------------------
-int am_count_matches_dev(const am_automaton* a, am_dev_text t, void* stream, uint64_t* out_count) {
-  int rc = check_ready(a); if (rc) return rc;
+int am_count_matches_dev(const am_automaton* a, int cs, const am_dev_text* t, void* stream, uint64_t* out_count) {
+  int rc = check_dev_text(t); if (rc) return rc;
   if (!out_count) return fail(AM_E_BADARG, "out_count is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(a, ws, t, MODE_COUNT, st);
+  rc = launch_scan(im, ws, *t, MODE_COUNT, st);
   if (!rc) rc = read_scalars(ws, st);
   if (!rc) *out_count = *reinterpret_cast<uint64_t*>(ws->h_scalars);
-  release_ws(a, ws);
+  release_ws(im, ws);
   return rc;
 }
 
-int am_contains_any_dev(const am_automaton* a, am_dev_text t, void* stream, int* out_bool) {
-  int rc = check_ready(a); if (rc) return rc;
+int am_contains_any_dev(const am_automaton* a, int cs, const am_dev_text* t, void* stream, int* out_bool) {
+  int rc = check_dev_text(t); if (rc) return rc;
   if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(a, ws, t, MODE_ANY, st);
+  rc = launch_scan(im, ws, *t, MODE_ANY, st);
   if (!rc) rc = read_scalars(ws, st);
   if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
-  release_ws(a, ws);
+  release_ws(im, ws);
   return rc;
 }
 
-int am_find_all_dev(const am_automaton* a, am_dev_text t, void* stream, am_match* dev_out, size_t cap, uint64_t* n_found) {
-  int rc = check_ready(a); if (rc) return rc;
-  if (!n_found) return fail(AM_E_BADARG, "n_found is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Shared tail of am_find_all_dev / am_find_all_sharded: the host has the counters; finish, check the capacity, unpack.
+static int finish_find_all_dev(const Image* im, Workspace* ws, const am_dev_text& t, cudaStream_t st, am_match* dev_out, size_t cap, uint64_t* n_found) {
   uint64_t n = 0;
   bool unpacked = false;
-  rc = find_all_sorted(a, ws, t, st, &n, dev_out, dev_out ? cap : 0, &unpacked);
-  if (!rc) {
-    *n_found = n;
-    if (n > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
-    else if (n > 0 && !unpacked) {
-      if (!dev_out) rc = fail(AM_E_BADARG, "dev_out is null");
-      else {
-        cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, dev_out, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) rc = cuda_fail(e, "unpack");
-      }
-    }
+  int rc = emit_finish(im, ws, t, st, &n, dev_out, dev_out ? cap : 0, &unpacked);
+  if (rc) return rc;
+  *n_found = n;
+  if (n > cap) return fail(AM_E_OVERFLOW, "output buffer too small");
+  if (n > 0 && !unpacked) {
+    if (!dev_out) return fail(AM_E_BADARG, "dev_out is null");
+    cudaError_t e = launch_unpack(ws->keys_b, n, im->host.rank_bits, im->dev.id_of_rank, dev_out, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "unpack");
   }
-  release_ws(a, ws);
+  return AM_OK;
+}
+
+int am_find_all_dev(const am_automaton* a, int cs, const am_dev_text* t, void* stream, am_match* dev_out, size_t cap, uint64_t* n_found) {
+  int rc = check_dev_text(t); if (rc) return rc;
+  if (!n_found) return fail(AM_E_BADARG, "n_found is null");
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t span = t->text_len - std::min(t->report_begin, t->text_len);
+  rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
+  if (!rc) rc = emit_enqueue(im, ws, *t, st, dev_out, dev_out ? cap : 0);
+  if (!rc) rc = read_scalars(ws, st);
+  if (!rc) rc = finish_find_all_dev(im, ws, *t, st, dev_out, cap, n_found);
+  release_ws(im, ws);
+  return rc;
+}
+
+// ---- multi-GPU: scan + all-gather of the counts, one host round trip (am_comm.cu holds the communicator) ---------------
+int am_count_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_text* shard, void* stream, am_shard_result* out) {
+  int rc = check_dev_text(shard); if (rc) return rc;
+  if (!out || !c) return fail(AM_E_BADARG, "null argument");
+  AM_ENTER(a, cs);
+  if ((rc = comm_check(c, im->device))) return rc;
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_scan(im, ws, *shard, MODE_COUNT, st);
+  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars, ws->d_scalars + 64, st);            // this rank's count -> every rank's
+  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+  if (!rc) comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), out);
+  release_ws(im, ws);
+  return rc;
+}
+
+int am_contains_any_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_text* shard, void* stream, int* out_bool) {
+  int rc = check_dev_text(shard); if (rc) return rc;
+  if (!out_bool || !c) return fail(AM_E_BADARG, "null argument");
+  AM_ENTER(a, cs);
+  if ((rc = comm_check(c, im->device))) return rc;
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_scan(im, ws, *shard, MODE_ANY, st);                                          // d_scalars[8..16): this shard's flag (0 / 1)
+  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 8, ws->d_scalars + 64, st);
+  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+  if (!rc) {
+    am_shard_result r;
+    comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), &r);
+    *out_bool = r.total != 0;
+  }
+  release_ws(im, ws);
+  return rc;
+}
+
+int am_find_all_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_text* shard, void* stream, am_match* dev_out, size_t cap, am_shard_result* out) {
+  int rc = check_dev_text(shard); if (rc) return rc;
+  if (!out || !c) return fail(AM_E_BADARG, "null argument");
+  AM_ENTER(a, cs);
+  if ((rc = comm_check(c, im->device))) return rc;
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t span = shard->text_len - std::min(shard->report_begin, shard->text_len);
+  rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
+  // scan, segment scan and segment sort are queued; the match count is d_scalars[0..8) + d_scalars[8..16) whatever path the
+  // ordering takes afterwards, so the all-gather goes on the stream right behind them and the host waits ONCE
+  if (!rc) rc = emit_enqueue(im, ws, *shard, st, dev_out, dev_out ? cap : 0);
+  if (!rc) {
+    cudaError_t e = launch_sum2(reinterpret_cast<const unsigned long long*>(ws->d_scalars), ws->emit_segmented ? 2 : 1,
+                                reinterpret_cast<unsigned long long*>(ws->d_scalars + 32), st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "count kernel");
+  }
+  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
+  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+  if (!rc) {
+    comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), out);
+    uint64_t n = 0;
+    rc = finish_find_all_dev(im, ws, *shard, st, dev_out, cap, &n);                        // (a rescan never changes the count)
+    if (n != out->n_local && (rc == AM_OK || rc == AM_E_OVERFLOW)) rc = fail(AM_E_INTERNAL, "sharded match count changed between scan and ordering");
+  }
+  release_ws(im, ws);
   return rc;
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------------------
-static int check_slice(const am_u8slice& s) {
-  if (s.len < 0 || s.off < 0 || (s.len > 0 && !s.ptr)) return fail(AM_E_BADARG, "bad text slice");
-  return AM_OK;
-}
 static int upload_text(Workspace* ws, const am_u8slice& hay, cudaStream_t st, am_dev_text* t) {
   int rc = ws->need_text((uint64_t)hay.len);
   if (rc) return rc;
@@ -537,9 +735,29 @@ static int upload_text(Workspace* ws, const am_u8slice& hay, cudaStream_t st, am
 }  // extern "C" (the chunk loop is a template)
 
 constexpr uint64_t HOST_CHUNK = 64ull << 20;
+constexpr uint64_t HOST_REGISTER_MIN = 256ull << 20;
+
+// A host text that is not page-locked (a GHC pinned ByteArray#, malloc, numpy) would make every cudaMemcpyAsync a staged,
+// synchronous copy.  Large texts are page-locked in place for the duration of the call; AM_HOST_REGISTER=0 turns it off.
+struct HostPin {
+  void* base = nullptr;
+  ~HostPin() { if (base) cudaHostUnregister(base); }
+  void pin(const uint8_t* p, uint64_t len) {
+    static const bool off = []() { const char* v = std::getenv("AM_HOST_REGISTER"); return v && std::atoi(v) == 0; }();
+    if (off || len < HOST_REGISTER_MIN) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeUnregistered) return;        // already page-locked (cudaHostAlloc / registered) or managed
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095), hi = (reinterpret_cast<uintptr_t>(p) + len + 4095) & ~uintptr_t(4095);
+    if (cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterReadOnly) == cudaSuccess) base = reinterpret_cast<void*>(lo);
+    else if (cudaGetLastError(), cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterDefault) == cudaSuccess) base = reinterpret_cast<void*>(lo);
+    else cudaGetLastError();                                  // could not pin: the copies are staged by the driver instead
+  }
+};
+
 // Calls fn(window, stream) for every chunk in order; fn returns < 0 to stop early (no error), 0 to go on, > 0 = error code.
 template <class F>
-static int for_each_host_chunk(const am_automaton* a, Workspace* ws, const am_u8slice& hay, F fn) {
+static int for_each_host_chunk(const Image* a, Workspace* ws, const am_u8slice& hay, F fn) {
   const uint64_t len = (uint64_t)hay.len;
   int rc = ws->need_text(len);
   if (rc) return rc;
@@ -555,6 +773,8 @@ static int for_each_host_chunk(const am_automaton* a, Workspace* ws, const am_u8
       return cuda_fail(cudaGetLastError(), "stream / event creation");
   }
   const uint8_t* src = hay.ptr + hay.off;
+  HostPin pin;
+  pin.pin(src, len);
   const uint64_t halo = a->host.halo_bytes;
   const uint64_t chunks = (len + HOST_CHUNK - 1) / HOST_CHUNK;
   auto upload = [&](uint64_t k) -> cudaError_t {
@@ -580,7 +800,7 @@ static int for_each_host_chunk(const am_automaton* a, Workspace* ws, const am_u8
   return rc < 0 ? AM_OK : rc;
 }
 
-static int scan_host_pipelined(const am_automaton* a, Workspace* ws, const am_u8slice& hay, int mode, uint64_t* out_count, int* out_any) {
+static int scan_host_pipelined(const Image* a, Workspace* ws, const am_u8slice& hay, int mode, uint64_t* out_count, int* out_any) {
   if (out_count) *out_count = 0;
   if (out_any) *out_any = 0;
   return for_each_host_chunk(a, ws, hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
@@ -595,42 +815,42 @@ static int scan_host_pipelined(const am_automaton* a, Workspace* ws, const am_u8
 
 extern "C" {
 
-int am_count_matches(const am_automaton* a, am_u8slice hay, uint64_t* out_count) {
-  int rc = check_ready(a); if (rc) return rc;
-  if ((rc = check_slice(hay))) return rc;
+int am_count_matches(const am_automaton* a, int cs, const am_u8slice* hay, uint64_t* out_count) {
+  int rc = check_slice(hay); if (rc) return rc;
   if (!out_count) return fail(AM_E_BADARG, "out_count is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  rc = scan_host_pipelined(a, ws, hay, MODE_COUNT, out_count, nullptr);
-  release_ws(a, ws);
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  rc = scan_host_pipelined(im, ws, *hay, MODE_COUNT, out_count, nullptr);
+  release_ws(im, ws);
   return rc;
 }
 
-int am_contains_any(const am_automaton* a, am_u8slice hay, int* out_bool) {
-  int rc = check_ready(a); if (rc) return rc;
-  if ((rc = check_slice(hay))) return rc;
+int am_contains_any(const am_automaton* a, int cs, const am_u8slice* hay, int* out_bool) {
+  int rc = check_slice(hay); if (rc) return rc;
   if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  rc = scan_host_pipelined(a, ws, hay, MODE_ANY, nullptr, out_bool);
-  release_ws(a, ws);
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  rc = scan_host_pipelined(im, ws, *hay, MODE_ANY, nullptr, out_bool);
+  release_ws(im, ws);
   return rc;
 }
 
-int am_find_all(const am_automaton* a, am_u8slice hay, am_match* out, size_t cap, uint64_t* n_found) {
-  int rc = check_ready(a); if (rc) return rc;
-  if ((rc = check_slice(hay))) return rc;
+int am_find_all(const am_automaton* a, int cs, const am_u8slice* hay, am_match* out, size_t cap, uint64_t* n_found) {
+  int rc = check_slice(hay); if (rc) return rc;
   if (!n_found) return fail(AM_E_BADARG, "n_found is null");
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  AM_ENTER(a, cs);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   // chunk by chunk (the lists of consecutive chunks concatenate: matches are partitioned by end position); each chunk's
   // records travel back while the next chunk is scanned and the one after that is uploaded
   uint64_t total = 0;
-  rc = for_each_host_chunk(a, ws, hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
+  rc = for_each_host_chunk(im, ws, *hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
     uint64_t n = 0;
-    int r = find_all_sorted(a, ws, t, st, &n);
+    int r = find_all_sorted(im, ws, t, st, &n);
     if (r) return r;
     if (n > 0 && total + n <= cap) {
       if (!out) return fail(AM_E_BADARG, "out is null");
       if ((r = ws->need_matches(n))) return r;
-      cudaError_t e = launch_unpack(ws->keys_b, n, a->host.rank_bits, a->dev.id_of_rank, ws->matches, st);
+      cudaError_t e = launch_unpack(ws->keys_b, n, im->host.rank_bits, im->dev.id_of_rank, ws->matches, st);
       if (e == cudaSuccess) e = cudaMemcpyAsync(out + total, ws->matches, n * sizeof(am_match), cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) return cuda_fail(e, "unpack / D2H");
     }
@@ -643,36 +863,41 @@ int am_find_all(const am_automaton* a, am_u8slice hay, am_match* out, size_t cap
     *n_found = total;
     if (!rc && total > cap) rc = fail(AM_E_OVERFLOW, "output buffer too small");
   }
-  release_ws(a, ws);
+  release_ws(im, ws);
   return rc;
 }
 
-int am_contains_all(const am_automaton* a, am_u8slice hay, int* out_bool) {
-  // Searcher.containsAll (Searcher.hs:173-187): every needle id must be seen at least once.
-  int rc = check_ready(a); if (rc) return rc;
-  if ((rc = check_slice(hay))) return rc;
+int am_contains_all(const am_automaton* a, int cs, const am_u8slice* hay, int* out_bool) {
+  // Searcher.containsAll (Searcher.hs:173-187): the set of outstanding needle ids starts full; every match removes its
+  // needle; the answer is "the set is empty" and the fold stops as soon as it is.  Here the set is a bit per needle rank in
+  // HBM: after each chunk's scan a kernel ORs in the ranks of the chunk's matches and counts the ranks still missing,
+  // and the upload stops at the first chunk after which none is.
+  int rc = check_slice(hay); if (rc) return rc;
   if (!out_bool) return fail(AM_E_BADARG, "out_bool is null");
-  const uint64_t nn = a->host.num_needles;
+  AM_ENTER(a, cs);
+  const uint64_t nn = im->host.num_needles;
   if (nn == 0) { *out_bool = 1; return AM_OK; }
-  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  am_dev_text t;
-  uint64_t n = 0;
-  rc = upload_text(ws, hay, 0, &t);
-  if (!rc) rc = find_all_sorted(a, ws, t, 0, &n);
-  if (!rc) {
-    std::vector<uint64_t> keys(n);
-    if (n) {
-      cudaError_t e = cudaMemcpy(keys.data(), ws->keys_b, n * 8, cudaMemcpyDeviceToHost);
-      if (e != cudaSuccess) rc = cuda_fail(e, "D2H keys");
-    }
-    if (!rc) {
-      std::vector<uint8_t> seen(nn, 0); uint64_t left = nn;
-      const uint64_t mask = (1ull << a->host.rank_bits) - 1;
-      for (uint64_t k : keys) { uint32_t r = (uint32_t)(k & mask); if (!seen[r]) { seen[r] = 1; left--; } }
-      *out_bool = left == 0;
-    }
-  }
-  release_ws(a, ws);
+  Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
+  rc = ws->need_seen(nn);
+  if (!rc && cudaMemsetAsync(ws->seen_bits, 0, (nn + 31) / 32 * 4, 0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
+  if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaMemsetAsync");
+  uint64_t missing = nn;
+  if (!rc)
+    rc = for_each_host_chunk(im, ws, *hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
+      uint64_t n = 0;
+      int r = find_all_sorted(im, ws, t, st, &n);
+      if (r) return r;
+      if (n == 0) return 0;
+      unsigned int* d_missing = reinterpret_cast<unsigned int*>(ws->d_scalars + 40);
+      cudaError_t e = launch_mark_seen(ws->keys_b, n, im->host.rank_bits, ws->seen_bits, (uint32_t)nn, d_missing, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 40, d_missing, 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "needle bit set");
+      missing = *reinterpret_cast<unsigned int*>(ws->h_scalars + 40);
+      return missing == 0 ? -1 : 0;                            // every needle seen: stop uploading (Searcher.hs:180-181)
+    });
+  if (!rc) *out_bool = missing == 0;
+  release_ws(im, ws);
   return rc;
 }
 
@@ -689,31 +914,31 @@ int am_shard_plan(uint64_t text_len, uint64_t halo_bytes, uint32_t n_shards, uin
   return AM_OK;
 }
 
-int am_lower_utf8(const am_lower_table* lower, am_u8slice text, uint8_t* out, size_t cap, uint64_t* out_len) {
+int am_lower_utf8(const am_lower_table* lower, const am_u8slice* text, uint8_t* out, size_t cap, uint64_t* out_len) {
   int rc = check_slice(text); if (rc) return rc;
   if (!out_len) return fail(AM_E_BADARG, "out_len is null");
   LowerTable lt;
   if ((rc = build_lower_table(lower, &lt))) return fail(rc, "bad lower table");
   std::vector<uint8_t> v;
-  lower_utf8_host(lt, text.ptr + text.off, text.len, &v);
+  lower_utf8_host(lt, text->ptr + text->off, text->len, &v);
   *out_len = v.size();
   if (v.size() > cap) return fail(AM_E_OVERFLOW, "output buffer too small");
   if (!v.empty()) { if (!out) return fail(AM_E_BADARG, "out is null"); std::memcpy(out, v.data(), v.size()); }
   return AM_OK;
 }
 
-int am_skip_code_points_backwards(am_u8slice text, int64_t index0, int64_t n0, int64_t* out_index) {
+int am_skip_code_points_backwards(const am_u8slice* text, int64_t index0, int64_t n0, int64_t* out_index) {
   // Utf8.hs:256-276
   int rc = check_slice(text); if (rc) return rc;
   if (!out_index) return fail(AM_E_BADARG, "out_index is null");
-  if (index0 >= text.len) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
-  const uint8_t* d = text.ptr;
-  int64_t index = index0 + text.off, n = n0;
+  if (index0 >= text->len) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
+  const uint8_t* d = text->ptr;
+  int64_t index = index0 + text->off, n = n0;
   for (;;) {
     if (index >= 0 && (d[index] & 0xC0) == 0x80) { index--; continue; }
     if (n == 0) {
       if (index < 0) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
-      *out_index = index - text.off; return AM_OK;
+      *out_index = index - text->off; return AM_OK;
     }
     if (index < 0) return fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards");
     index--; n--;
@@ -721,18 +946,26 @@ int am_skip_code_points_backwards(am_u8slice text, int64_t index0, int64_t n0, i
 }
 
 void am_free(void* p) { std::free(p); }
+void am_dev_free(void* p) { if (p) cudaFree(p); }
 
 int am_profile_enable(int on) { g_profile.store(on ? 1 : 0); return AM_OK; }
 int am_profile_last_scan_ms(float* ms) {
   if (!ms) return fail(AM_E_BADARG, "ms is null");
-  if (!g_ev_valid) return fail(AM_E_BADARG, "no profiled scan on this thread");
-  cudaError_t e = cudaEventSynchronize(g_ev1);
+  if (!g_ev0 || g_ev_device < 0) return fail(AM_E_BADARG, "no profiled scan on this thread");
+  DeviceGuard g;
+  cudaError_t e = g.enter(g_ev_device);
+  if (e == cudaSuccess) e = cudaEventSynchronize(g_ev1);
   if (e == cudaSuccess) e = cudaEventElapsedTime(ms, g_ev0, g_ev1);
   return e == cudaSuccess ? AM_OK : cuda_fail(e, "event timing");
 }
 uint64_t am_profile_kernel_launches(void) { return g_kernel_launches.load(); }
 uint64_t am_replacer_last_passes(void) { return g_last_passes; }
 uint64_t am_replacer_last_rescans(void) { return g_last_rescans; }
+int am_replacer_last_profile(float* ms, uint64_t* bytes_moved) {
+  if (ms) *ms = g_last_replacer_ms;
+  if (bytes_moved) *bytes_moved = g_last_replacer_bytes;
+  return AM_OK;
+}
 
 // ---- synthetic workloads ----------------------------------------------------------------------------------------------
 int am_synth_fill_dev(void* dev_buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* alphabet, uint32_t alphabet_len, void* stream) {

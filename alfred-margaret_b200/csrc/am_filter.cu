@@ -456,11 +456,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
 template <int MODE, bool Q4, bool T2X, int CASE>
 static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   if (a.text_len <= a.report_begin) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(filter_kernel<MODE, Q4, T2X, CASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FilterSmem));
+  static std::atomic<uint64_t> attr_done{0};   // per device (am_options.device: one process may use several GPUs)
+  {
+    cudaError_t e = ensure_dynamic_smem(filter_kernel<MODE, Q4, T2X, CASE>, (int)sizeof(FilterSmem), attr_done);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
   // first start position that can produce a match ending after report_begin

@@ -388,11 +388,10 @@ __global__ void unpack_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bi
 template <bool IC, int MODE>
 static cudaError_t launch_walk_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   if (a.text_len <= a.report_begin) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(walk_kernel<IC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WalkSmem) + WALK_HOT_BYTES_BIG));
+  static std::atomic<uint64_t> attr_done{0};   // per device (am_options.device: one process may use several GPUs)
+  {
+    cudaError_t e = ensure_dynamic_smem(walk_kernel<IC, MODE>, (int)(sizeof(WalkSmem) + WALK_HOT_BYTES_BIG), attr_done);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const uint64_t span = a.text_len - a.report_begin;
   // small automaton: one big CTA per SM with most rows in shared memory; large: two CTAs, rows mostly via L1/L2
@@ -522,6 +521,52 @@ cudaError_t launch_seg_compact(const uint64_t* seg_keys, const uint32_t* seg_cou
   const unsigned blocks = (unsigned)std::min<uint64_t>((num_segs * 32 + 255) / 256 + (n_ovf + 255) / 256, (uint64_t)sm_count() * 8);
   g_kernel_launches++;
   seg_compact_kernel<<<blocks ? blocks : 1, 256, 0, st>>>(seg_keys, seg_counts, bases, num_segs, seg_cap, ovf_keys, n_ovf, stored_total, out);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// small helpers of the sharded calls and of containsAll
+// =====================================================================================================
+__global__ void sum2_kernel(const unsigned long long* in, int n, unsigned long long* out) {
+  unsigned long long s = 0;
+  for (int i = 0; i < n; i++) s += in[i];
+  *out = s;
+}
+cudaError_t launch_sum2(const unsigned long long* d_in, int n, unsigned long long* d_out, cudaStream_t st) {
+  g_kernel_launches++;
+  sum2_kernel<<<1, 1, 0, st>>>(d_in, n, d_out);
+  return cudaGetLastError();
+}
+
+// Searcher.containsAll (Searcher.hs:173-187): OR the needle ranks of a sorted key list into a bit set ...
+__global__ void mark_seen_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bits, uint32_t* seen) {
+  const uint64_t mask = (1ull << rank_bits) - 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(keys[i] & mask);
+    const uint32_t bit = 1u << (r & 31);
+    if (!(seen[r >> 5] & bit)) atomicOr(seen + (r >> 5), bit);
+  }
+}
+// ... and count the needles that have not been seen yet.
+__global__ void count_missing_kernel(const uint32_t* seen, uint32_t num_needles, unsigned int* missing) {
+  __shared__ unsigned int red[32];
+  const uint32_t words = (num_needles + 31) / 32;
+  unsigned int local = 0;
+  for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) local += __popc(seen[w]);
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int s = 0;
+    for (unsigned i = 0; i < blockDim.x / 32; i++) s += red[i];
+    *missing = num_needles - s;
+  }
+}
+cudaError_t launch_mark_seen(const uint64_t* keys, uint64_t n, uint32_t rank_bits, uint32_t* seen, uint32_t num_needles, unsigned int* d_missing, cudaStream_t st) {
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count() * 8);
+  g_kernel_launches += 2;
+  if (n) mark_seen_kernel<<<blocks, 256, 0, st>>>(keys, n, rank_bits, seen);
+  count_missing_kernel<<<1, 1024, 0, st>>>(seen, num_needles, d_missing);
   return cudaGetLastError();
 }
 

@@ -11,15 +11,30 @@ namespace am {
 
 extern std::atomic<uint64_t> g_kernel_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
-// SM count of the current device (grids are sized as one persistent CTA, or two, per SM).
+// SM count of the current device (grids are sized as one persistent CTA, or two, per SM).  Cached per device: one
+// process may drive several GPUs (am_options.device).
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0; cudaGetDevice(&dev);
+  static std::atomic<int> cache[64];
+  int dev = 0; cudaGetDevice(&dev);
+  const int slot = dev & 63;
+  int n = cache[slot].load(std::memory_order_relaxed);
+  if (n <= 0) {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE (per-context) attribute of a kernel: opt in once per
+// (kernel, device).  `done` is one mask per kernel instantiation (a function-local static of the caller), bit = device.
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0; cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 // Per-segment goto+failure walk (general path).  mode: ScanMode.
@@ -44,6 +59,10 @@ size_t sort_temp_bytes(uint64_t n, int end_bit);
 cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_t* out, uint64_t n, int end_bit, cudaStream_t st);
 cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st);
 int filter_kernel_smem_bytes();
+// out = in[0] + ... + in[n - 1] (one thread; joins the counters of a scan on the stream, ahead of the sharded calls' all-gather)
+cudaError_t launch_sum2(const unsigned long long* d_in, int n, unsigned long long* d_out, cudaStream_t st);
+// containsAll: OR the needle ranks of keys[0..n) into the bit set `seen`, then *d_missing = needles not seen yet
+cudaError_t launch_mark_seen(const uint64_t* keys, uint64_t n, uint32_t rank_bits, uint32_t* seen, uint32_t num_needles, unsigned int* d_missing, cudaStream_t st);
 
 // synthetic workload generator (am_synth.cu)
 cudaError_t launch_synth_fill(uint8_t* buf, uint64_t len, uint64_t first, uint64_t seed, const uint8_t* d_alpha, uint32_t alpha_len, cudaStream_t st);

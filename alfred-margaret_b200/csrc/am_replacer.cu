@@ -25,13 +25,14 @@
 using namespace am;
 
 struct am_replacer {
-  am_automaton* automaton = nullptr;
-  int cs = AM_CASE_SENSITIVE;
+  am_automaton* automaton = nullptr;     // over the needles as `build` stores them: lowered iff built with IgnoreCase (:105-107)
+  int built_cs = AM_CASE_SENSITIVE;
   uint64_t n = 0;
-  std::vector<uint32_t> len_bytes, len_cps, repl_off;   // per needle index
+  std::vector<uint32_t> len_bytes, len_cps, repl_off;   // Payload of needle i: lengths of the ORIGINAL needle (:111-113)
   std::vector<uint8_t> repl_bytes;
   uint8_t* d_repl = nullptr;
   bool has_empty = false;
+  bool stored_len_differs = false;       // some stored (lowered) needle has another byte length than the original
 };
 
 namespace {
@@ -74,7 +75,8 @@ __global__ void starts_kernel(const uint64_t* sel, uint64_t n, uint32_t rank_bit
     const uint64_t pos = sel[i] >> rank_bits;
     uint64_t s;
     if (!ignore_case) {
-      s = pos - len_bytes;                                   // makeMatch CaseSensitive (:268-269)
+      if (pos < len_bytes) { *error = 1; s = 0; }            // (only a replacer switched to the other case mode after build can get here)
+      else s = pos - len_bytes;                              // makeMatch CaseSensitive (:268-269)
     } else {
       // makeMatch IgnoreCase (:271-274): skipCodePointsBackwards haystack (pos - 1) (lenc - 1)
       long long idx = (long long)pos - 1, k = (long long)len_cps - 1;
@@ -265,76 +267,18 @@ __global__ void rescan_edits_kernel(DevAutomaton A, const uint8_t* text, uint64_
 
 }  // namespace
 
-extern "C" {
-
-int am_replacer_build(const am_u8slice* needles, const am_u8slice* repls, size_t n, int cs, const am_lower_table* lower,
-                      const am_options* opts, am_replacer** out) {
-  if (!out) return fail(AM_E_BADARG, "out is null");
-  *out = nullptr;
-  if (n > 0 && (!needles || !repls)) return fail(AM_E_BADARG, "needles / replacements is null");
-  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) return fail(AM_E_BADARG, "unknown case sensitivity");
-  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table");
-  am_replacer* r = new am_replacer();
-  r->cs = cs; r->n = n;
-  LowerTable lt;
-  int rc = build_lower_table(cs == AM_IGNORE_CASE ? lower : nullptr, &lt);
-  if (rc) { delete r; return fail(rc, "bad lower table"); }
-  std::vector<std::vector<uint8_t>> built(n);
-  std::vector<am_u8slice> slices(n);
-  r->repl_off.assign(n + 1, 0);
-  for (size_t i = 0; i < n; i++) {
-    if (needles[i].len < 0 || repls[i].len < 0 || (needles[i].len && !needles[i].ptr) || (repls[i].len && !repls[i].ptr)) { delete r; return fail(AM_E_BADARG, "bad slice"); }
-    const uint8_t* d = needles[i].ptr + needles[i].off;
-    uint32_t cps = 0;
-    for (int64_t k = 0; k < needles[i].len; k++) cps += (d[k] & 0xC0) != 0x80;
-    r->len_bytes.push_back((uint32_t)needles[i].len);            // needleLengthBytes of the ORIGINAL needle (:112)
-    r->len_cps.push_back(cps);                                    // needleLengthCodePoints (:113)
-    if (needles[i].len == 0) r->has_empty = true;
-    if (cs == AM_IGNORE_CASE) lower_utf8_host(lt, d, needles[i].len, &built[i]);   // Utf8.lowerUtf8 needle (:107)
-    else built[i].assign(d, d + needles[i].len);
-    slices[i] = am_u8slice{built[i].data(), 0, (int64_t)built[i].size()};
-    r->repl_bytes.insert(r->repl_bytes.end(), repls[i].ptr + repls[i].off, repls[i].ptr + repls[i].off + repls[i].len);
-    r->repl_off[i + 1] = (uint32_t)r->repl_bytes.size();
-  }
-  if (cs == AM_IGNORE_CASE && r->has_empty) {
-    delete r;
-    return fail(AM_E_UNSUPPORTED, "empty needle in an IgnoreCase replacer: the reference's skipCodePointsBackwards diverges on it");
-  }
-  rc = am_automaton_build(slices.data(), n, cs, lower, opts, &r->automaton);
-  if (rc) { delete r; return rc; }
-  if (r->automaton->device >= 0) {
-    cudaSetDevice(r->automaton->device);
-    if (cudaMalloc((void**)&r->d_repl, r->repl_bytes.size() + 16) != cudaSuccess) { cudaGetLastError(); am_replacer_free(r); return fail(AM_E_OOM, "cudaMalloc(replacements)"); }
-    if (!r->repl_bytes.empty()) cudaMemcpy(r->d_repl, r->repl_bytes.data(), r->repl_bytes.size(), cudaMemcpyHostToDevice);
-  }
-  *out = r;
-  return AM_OK;
-}
-
-void am_replacer_free(am_replacer* r) {
-  if (!r) return;
-  if (r->d_repl) cudaFree(r->d_repl);
-  if (r->automaton) am_automaton_free(r->automaton);
-  delete r;
-}
-
-int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint8_t** out, uint64_t* out_len, int* exceeded) {
-  if (!r || !out || !out_len || !exceeded) return fail(AM_E_BADARG, "null argument");
-  if (hay.len < 0 || hay.off < 0 || (hay.len > 0 && !hay.ptr)) return fail(AM_E_BADARG, "bad text slice");
-  const am_automaton* a = r->automaton;
-  int rc = check_ready(a); if (rc) return rc;
-  *out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0;
+// Replacer.runWithLimit (:203-242) on a device-resident text.  `d_in` is only read; the result is left in a buffer of the
+// library's: *d_out (cudaMalloc'ed, ownership passes to the caller), *out_len.
+static int replacer_core(const am_replacer* r, const Image* a, int cs, const uint8_t* d_in, uint64_t len, uint64_t max_len, cudaStream_t st,
+                         uint8_t** d_out, uint64_t* out_len, int* exceeded) {
+  *d_out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0; g_last_rescans = 0;
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  cudaStream_t st = 0;
   DevBuf text_a, text_b, sel, starts, ends, keep, kidx, kstart, kend, kdelta, kshift, cubtmp, scal;
-  uint64_t len = (uint64_t)hay.len;
+  int rc;
   auto done = [&](int code) { release_ws(a, ws); return code; };
-  if ((rc = text_a.ensure(len + 64)) || (rc = scal.ensure(64))) return done(rc);
-  if (len) {
-    cudaError_t e = cudaMemcpyAsync(text_a.p, hay.ptr + hay.off, len, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return done(cuda_fail(e, "H2D text"));
-  }
-  DevBuf* cur = &text_a; DevBuf* nxt = &text_b;
+  if ((rc = scal.ensure(64))) return done(rc);
+  const uint8_t* cur = d_in;                       // the current text; text_a / text_b are the library's ping-pong buffers
+  DevBuf* nxt = &text_a;
   const uint32_t rank_bits = a->host.rank_bits;
   const uint64_t mask = (1ull << rank_bits) - 1;
   long long prev_id = -1;                          // threshold 1 keeps every priority (:211)
@@ -347,14 +291,13 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
   // the reference's literal pass structure (a full scan per pass) for A/B runs
   const char* env_rescan = std::getenv("AM_REPLACER_RESCAN");   // read per call so that tests can A/B both forms
   const bool force_rescan = env_rescan && std::atoi(env_rescan) != 0;
-  const bool incremental = r->cs == AM_CASE_SENSITIVE && !r->has_empty && !force_rescan;
+  const bool incremental = cs == AM_CASE_SENSITIVE && !r->has_empty && !r->stored_len_differs && !force_rescan;
   bool have_list = false;
   uint64_t n = 0;
-  g_last_rescans = 0;
   for (;;) {
     // ---- 1. the matches of the current text: a full scan, or the list carried over from the previous pass ---------
     if (!have_list) {
-      am_dev_text t{cur->p, len, 0, 0};
+      am_dev_text t{cur, len, 0, 0};
       if ((rc = find_all_sorted(a, ws, t, st, &n))) return done(rc);
       g_last_rescans++;
     }
@@ -391,7 +334,7 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
     {
       unsigned blocks = (unsigned)std::min<uint64_t>((ns + 127) / 128, 148 * 8);
       g_kernel_launches++;
-      starts_kernel<<<blocks, 128, 0, st>>>(sel.as<uint64_t>(), ns, rank_bits, cur->as<uint8_t>(), r->cs == AM_IGNORE_CASE, r->len_bytes[id], r->len_cps[id],
+      starts_kernel<<<blocks, 128, 0, st>>>(sel.as<uint64_t>(), ns, rank_bits, cur, cs == AM_IGNORE_CASE, r->len_bytes[id], r->len_cps[id],
                                             (long long)rl, starts.as<uint64_t>(), ends.as<uint64_t>(), &d_s->delta_sum, &d_s->error);
     }
     // ---- 4. replacementLength over the un-deoverlapped matches (:240) -----------------------------------
@@ -440,19 +383,18 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
       uint64_t tiles = (len + SPLICE_TILE - 1) / SPLICE_TILE;
       if (tiles == 0) tiles = 1;                                  // empty text with an empty-needle match
       g_kernel_launches++;
-      splice_kernel<<<(unsigned)tiles, 256, 0, st>>>(cur->as<uint8_t>(), len, nxt->as<uint8_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), kshift.as<long long>(), K,
+      splice_kernel<<<(unsigned)tiles, 256, 0, st>>>(cur, len, nxt->as<uint8_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), kshift.as<long long>(), K,
                                                      r->d_repl + r->repl_off[id], rl, total_shift);
       if ((e = cudaGetLastError()) != cudaSuccess) return done(cuda_fail(e, "splice launch"));
     }
-    std::swap(cur, nxt);
-    const uint64_t old_len = len;
+    cur = nxt->as<uint8_t>();
+    nxt = nxt == &text_a ? &text_b : &text_a;
     len = new_len;
     if ((long long)id == last_id) break;           // p == minPriority: no needle is left (:241)
     prev_id = id;                                   // go p (:242)
     // ---- 7. the next pass's matches without a rescan ----------------------------------------------------------
     have_list = false;
     if (incremental) {
-      (void)old_len;
       const uint64_t cap = ws->keys_a_bytes / 8;
       unsigned long long* d_n = reinterpret_cast<unsigned long long*>(ws->d_scalars);
       cudaMemsetAsync(d_n, 0, 8, st);
@@ -465,7 +407,7 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
       if (K) {
         unsigned blocks = (unsigned)std::min<uint64_t>((K + 63) / 64, 148 * 16);
         g_kernel_launches++;
-        rescan_edits_kernel<<<blocks, 64, 0, st>>>(a->dev, cur->as<uint8_t>(), len, kstart.as<uint64_t>(), kshift.as<long long>(), K, rl, id, ws->keys_a, d_n, cap);
+        rescan_edits_kernel<<<blocks, 64, 0, st>>>(a->dev, cur, len, kstart.as<uint64_t>(), kshift.as<long long>(), K, rl, id, ws->keys_a, d_n, cap);
       }
       unsigned long long n_new = 0;
       cudaMemcpyAsync(&n_new, d_n, 8, cudaMemcpyDeviceToHost, st);
@@ -484,14 +426,153 @@ int am_replacer_run(const am_replacer* r, am_u8slice hay, uint64_t max_len, uint
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return done(cuda_fail(e, "replacer"));
-  uint8_t* host = static_cast<uint8_t*>(std::malloc(len ? len : 1));
-  if (!host) return done(fail(AM_E_OOM, "malloc(result)"));
-  if (len) {
-    e = cudaMemcpy(host, cur->p, len, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { std::free(host); return done(cuda_fail(e, "D2H result")); }
+  // hand the result buffer over: the ping-pong buffer that holds it, or a copy of the (untouched) input
+  DevBuf* holder = cur == text_a.p ? &text_a : cur == text_b.p ? &text_b : nullptr;
+  if (holder) { *d_out = holder->as<uint8_t>(); holder->p = nullptr; holder->cap = 0; }
+  else {
+    void* p = nullptr;
+    if (cudaMalloc(&p, len + 64) != cudaSuccess) { cudaGetLastError(); return done(fail(AM_E_OOM, "cudaMalloc(result)")); }
+    if (len && (e = cudaMemcpyAsync(p, cur, len, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) { cudaFree(p); return done(cuda_fail(e, "result copy")); }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaFree(p); return done(cuda_fail(e, "result copy")); }
+    *d_out = static_cast<uint8_t*>(p);
   }
-  *out = host; *out_len = len;
+  *out_len = len;
   return done(AM_OK);
+}
+
+extern "C" {
+
+void am_replacer_free(am_replacer* r);
+
+// The stored form of a Replacer: the needles exactly as its searcher holds them (lowered iff it was built with
+// IgnoreCase, :105-107) and the Payload lengths of the ORIGINAL needles (:111-113).  `build` derives it; `compose`
+// (:120-133), `mapReplacement` (:136-141) and the derived FromJSON instance start from it and lower nothing.
+static int replacer_from_stored(const am_u8slice* stored, const uint32_t* len_bytes, const uint32_t* len_cps, const am_u8slice* repls, size_t n,
+                                int prepare_cs, const am_lower_table* lower, const am_options* opts, am_replacer** out) {
+  am_replacer* r = new am_replacer();
+  r->built_cs = prepare_cs; r->n = n;
+  r->repl_off.assign(n + 1, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (stored[i].len < 0 || repls[i].len < 0 || stored[i].off < 0 || repls[i].off < 0 || (stored[i].len && !stored[i].ptr) || (repls[i].len && !repls[i].ptr)) { delete r; return fail(AM_E_BADARG, "bad slice"); }
+    r->len_bytes.push_back(len_bytes[i]);
+    r->len_cps.push_back(len_cps[i]);
+    if (stored[i].len == 0) r->has_empty = true;
+    if ((uint64_t)stored[i].len != len_bytes[i]) r->stored_len_differs = true;
+    r->repl_bytes.insert(r->repl_bytes.end(), repls[i].ptr + repls[i].off, repls[i].ptr + repls[i].off + repls[i].len);
+    r->repl_off[i + 1] = (uint32_t)r->repl_bytes.size();
+  }
+  int rc = am_automaton_build(stored, n, lower, opts, &r->automaton);
+  if (!rc && !(prepare_cs == AM_IGNORE_CASE && r->has_empty)) rc = am_automaton_prepare(r->automaton, prepare_cs);
+  if (rc) { am_replacer_free(r); return rc; }
+  if (r->automaton->device >= 0) {
+    DeviceGuard g;
+    g.enter(r->automaton->device);
+    if (cudaMalloc((void**)&r->d_repl, r->repl_bytes.size() + 16) != cudaSuccess) { cudaGetLastError(); am_replacer_free(r); return fail(AM_E_OOM, "cudaMalloc(replacements)"); }
+    if (!r->repl_bytes.empty()) cudaMemcpy(r->d_repl, r->repl_bytes.data(), r->repl_bytes.size(), cudaMemcpyHostToDevice);
+  }
+  *out = r;
+  return AM_OK;
+}
+
+int am_replacer_build_stored(const am_u8slice* stored, const uint32_t* len_bytes, const uint32_t* len_cps, const am_u8slice* repls, size_t n,
+                             int cs, const am_lower_table* lower, const am_options* opts, am_replacer** out) {
+  if (!out) return fail(AM_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n > 0 && (!stored || !repls || !len_bytes || !len_cps)) return fail(AM_E_BADARG, "null argument");
+  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) return fail(AM_E_BADARG, "unknown case sensitivity");
+  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table");
+  return replacer_from_stored(stored, len_bytes, len_cps, repls, n, cs, lower, opts, out);
+}
+
+int am_replacer_build(const am_u8slice* needles, const am_u8slice* repls, size_t n, int cs, const am_lower_table* lower,
+                      const am_options* opts, am_replacer** out) {
+  if (!out) return fail(AM_E_BADARG, "out is null");
+  *out = nullptr;
+  if (n > 0 && (!needles || !repls)) return fail(AM_E_BADARG, "needles / replacements is null");
+  if (cs != AM_CASE_SENSITIVE && cs != AM_IGNORE_CASE) return fail(AM_E_BADARG, "unknown case sensitivity");
+  if (cs == AM_IGNORE_CASE && !lower) return fail(AM_E_BADARG, "IgnoreCase needs the Char.toLower table");
+  LowerTable lt;
+  int rc = build_lower_table(cs == AM_IGNORE_CASE ? lower : nullptr, &lt);
+  if (rc) return fail(rc, "bad lower table");
+  std::vector<std::vector<uint8_t>> built(n);
+  std::vector<am_u8slice> slices(n);
+  std::vector<uint32_t> lb(n), lc(n);
+  for (size_t i = 0; i < n; i++) {
+    if (needles[i].len < 0 || needles[i].off < 0 || (needles[i].len && !needles[i].ptr)) return fail(AM_E_BADARG, "bad slice");
+    const uint8_t* d = needles[i].ptr + needles[i].off;
+    uint32_t cps = 0;
+    for (int64_t k = 0; k < needles[i].len; k++) cps += (d[k] & 0xC0) != 0x80;
+    lb[i] = (uint32_t)needles[i].len;                             // needleLengthBytes of the ORIGINAL needle (:112)
+    lc[i] = cps;                                                  // needleLengthCodePoints (:113)
+    if (cs == AM_IGNORE_CASE) lower_utf8_host(lt, d, needles[i].len, &built[i]);   // Utf8.lowerUtf8 needle (:107)
+    else built[i].assign(d, d + needles[i].len);
+    slices[i] = am_u8slice{built[i].data(), 0, (int64_t)built[i].size()};
+  }
+  if (cs == AM_IGNORE_CASE)
+    for (size_t i = 0; i < n; i++)
+      if (needles[i].len == 0)
+        return fail(AM_E_UNSUPPORTED, "empty needle in an IgnoreCase replacer: the reference's skipCodePointsBackwards diverges on it");
+  return replacer_from_stored(slices.data(), lb.data(), lc.data(), repls, n, cs, lower, opts, out);
+}
+
+void am_replacer_free(am_replacer* r) {
+  if (!r) return;
+  if (r->d_repl) {
+    DeviceGuard g;
+    if (r->automaton && r->automaton->device >= 0) g.enter(r->automaton->device);
+    cudaFree(r->d_repl);
+  }
+  if (r->automaton) am_automaton_free(r->automaton);
+  delete r;
+}
+
+static int replacer_enter(const am_replacer* r, int cs, Image** im, DeviceGuard* g) {
+  if (!r) return fail(AM_E_BADARG, "replacer is null");
+  int rc = get_image(r->automaton, cs, im);
+  if (rc) return rc;
+  if (cs == AM_IGNORE_CASE && r->has_empty)
+    return fail(AM_E_UNSUPPORTED, "empty needle in an IgnoreCase replacer: the reference's skipCodePointsBackwards diverges on it");
+  return check_ready(*im, g);
+}
+
+int am_replacer_run_dev(const am_replacer* r, int cs, const void* dev_text, uint64_t text_len, uint64_t max_len, void* stream, void** dev_out,
+                        uint64_t* out_len, int* exceeded) {
+  if (!dev_out || !out_len || !exceeded) return fail(AM_E_BADARG, "null argument");
+  if (text_len > 0 && !dev_text) return fail(AM_E_BADARG, "dev_text is null");
+  Image* im = nullptr; DeviceGuard guard;
+  int rc = replacer_enter(r, cs, &im, &guard); if (rc) return rc;
+  uint8_t* d = nullptr;
+  rc = replacer_core(r, im, cs, static_cast<const uint8_t*>(dev_text), text_len, max_len, static_cast<cudaStream_t>(stream), &d, out_len, exceeded);
+  *dev_out = d;
+  return rc;
+}
+
+int am_replacer_run(const am_replacer* r, int cs, const am_u8slice* hay, uint64_t max_len, uint8_t** out, uint64_t* out_len, int* exceeded) {
+  if (!out || !out_len || !exceeded || !hay) return fail(AM_E_BADARG, "null argument");
+  if (hay->len < 0 || hay->off < 0 || (hay->len > 0 && !hay->ptr)) return fail(AM_E_BADARG, "bad text slice");
+  Image* im = nullptr; DeviceGuard guard;
+  int rc = replacer_enter(r, cs, &im, &guard); if (rc) return rc;
+  *out = nullptr; *out_len = 0; *exceeded = 0;
+  const uint64_t len = (uint64_t)hay->len;
+  DevBuf in;
+  if ((rc = in.ensure(len + 64))) return rc;
+  cudaStream_t st = 0;
+  if (len) {
+    cudaError_t e = cudaMemcpyAsync(in.p, hay->ptr + hay->off, len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D text");
+  }
+  uint8_t* d = nullptr; uint64_t n = 0;
+  rc = replacer_core(r, im, cs, in.as<uint8_t>(), len, max_len, st, &d, &n, exceeded);
+  if (rc || *exceeded) { if (d) cudaFree(d); return rc; }
+  uint8_t* host = static_cast<uint8_t*>(std::malloc(n ? n : 1));
+  if (!host) { cudaFree(d); return fail(AM_E_OOM, "malloc(result)"); }
+  if (n) {
+    cudaError_t e = cudaMemcpy(host, d, n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { std::free(host); cudaFree(d); return cuda_fail(e, "D2H result"); }
+  }
+  cudaFree(d);
+  *out = host; *out_len = n;
+  return AM_OK;
 }
 
 }  // extern "C"

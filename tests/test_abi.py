@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libam_b200.so does not export %s" % n
     assert sorted(_ffi.SYMBOLS) == names, "python binding and header disagree"
-    assert L.am_abi_version() == 1
+    assert L.am_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -67,12 +67,22 @@ def test_bad_arguments():
     from alfred_margaret_b200 import _ffi
     L = _ffi.lib()
     h = C.c_void_p()
-    assert L.am_automaton_build(None, 3, 0, None, None, C.byref(h)) == _ffi.AM_E_BADARG
-    assert L.am_automaton_build(None, 0, 7, None, None, C.byref(h)) == _ffi.AM_E_BADARG
-    assert L.am_automaton_build(None, 0, 1, None, None, C.byref(h)) == _ffi.AM_E_BADARG   # IgnoreCase without table
+    assert L.am_automaton_build(None, 3, None, None, C.byref(h)) == _ffi.AM_E_BADARG
+    opts = _ffi.Options(-2, 0, (C.c_uint64 * 6)())
+    assert L.am_automaton_build(None, 0, None, C.byref(opts), C.byref(h)) == _ffi.AM_OK   # no toLower table: a CaseSensitive-only handle
+    assert L.am_automaton_prepare(h, 7) == _ffi.AM_E_BADARG
+    assert L.am_automaton_prepare(h, 1) == _ffi.AM_E_BADARG                               # IgnoreCase without table
     assert b"toLower" in L.am_last_error()
+    buf = C.create_string_buffer(8)
+    assert L.am_last_error_copy(buf, 8) > 8 and buf.value == L.am_last_error()[:7]        # truncated, NUL-terminated
+    assert L.am_automaton_prepare(h, 0) == _ffi.AM_OK
+    L.am_automaton_free(h)
     n = C.c_uint64()
-    assert L.am_count_matches(None, _ffi.U8Slice(0, 0, 0), C.byref(n)) == _ffi.AM_E_BADARG
+    sl = _ffi.U8Slice(0, 0, 0)
+    assert L.am_count_matches(None, 0, C.byref(sl), C.byref(n)) == _ffi.AM_E_BADARG
+    assert L.am_count_matches(None, 0, None, C.byref(n)) == _ffi.AM_E_BADARG
+    c = C.c_void_p()
+    assert L.am_comm_init(3, 2, None, -1, C.byref(c)) == _ffi.AM_E_BADARG                 # rank >= nranks
 
 
 def test_lower_utf8_and_pins(golden, oracle, lower_dense):
@@ -219,16 +229,16 @@ int main(void) {
   for (int i = 0; i < 3; i++) { needles[i].ptr = (const uint8_t *)n[i]; needles[i].off = 0; needles[i].len = (int64_t)strlen(n[i]); }
   am_options opts; memset(&opts, 0, sizeof opts); opts.device = -2;            /* host image only */
   am_automaton *a = 0;
-  if (am_abi_version() != 1) return 2;
-  if (am_automaton_build(needles, 3, AM_CASE_SENSITIVE, 0, &opts, &a) != AM_OK) { printf("%s\n", am_last_error()); return 3; }
+  if (am_abi_version() != 2) return 2;
+  if (am_automaton_build(needles, 3, 0, &opts, &a) != AM_OK) { printf("%s\n", am_last_error()); return 3; }
   uint64_t states = 0, maxlen = 0, halo = 0; int kind = 0;
-  if (am_automaton_info(a, &states, &maxlen, &halo, &kind) != AM_OK) return 4;
+  if (am_automaton_info(a, AM_CASE_SENSITIVE, &states, &maxlen, &halo, &kind) != AM_OK) return 4;
   const char *text = "short tshirts";
   am_u8slice hay = {(const uint8_t *)text, 0, 13};
   uint8_t flags[13];
-  if (am_debug_host_filter(a, hay, 0, flags) != AM_OK) return 5;
+  if (am_debug_host_filter(a, AM_CASE_SENSITIVE, &hay, 0, flags) != AM_OK) return 5;
   uint64_t cnt = 0;
-  int rc = am_count_matches(a, hay, &cnt);                                      /* no device: must refuse, not fall back */
+  int rc = am_count_matches(a, AM_CASE_SENSITIVE, &hay, &cnt);                  /* no device: must refuse, not fall back */
   printf("%llu %llu %llu %d %d %d\n", (unsigned long long)states, (unsigned long long)maxlen, (unsigned long long)halo, kind, (flags[6] & 3) == 3, rc == AM_E_NODEVICE);
   am_automaton_free(a);
   return 0;
@@ -237,9 +247,6 @@ int main(void) {
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
                            "-L", lib_dir, "-lam_b200", "-Wl,-rpath," + lib_dir])
-    # the by-pointer wrappers the Haskell shim imports (GHC cannot pass a struct by value) compile against the same header
-    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-c",
-                           os.path.join(root, "alfred-margaret_b200", "haskell", "cbits", "am_shim.c"), "-o", str(tmp_path / "am_shim.o")])
     out = subprocess.check_output([str(exe)], text=True).split()
     # 17 states (tshirt 6 + shirts 6 + shorts 4 new + root), longest needle 6, halo 5, filter kernel; "tshirts" starts at 6
     assert out == ["17", "6", "5", "2", "1", "1"], out

@@ -77,8 +77,60 @@ def test_run_text_fold_and_early_exit(am):
     assert first == (10, "T")
     n = A.run_text(0, lambda a, _: A.Step(a + 1), m, "short tshirts")
     assert n == 2
-    with pytest.raises(ValueError):
-        A.run_lower(0, lambda a, _: A.Step(a + 1), m, "x")
+    # the SAME machine runs in the other case mode too, with no rebuild (Automaton.hs:539-553)
+    assert A.run_lower(0, lambda a, _: A.Step(a + 1), m, "Short TSHIRTS") == 2
+    assert A.run_text(0, lambda a, _: A.Step(a + 1), m, "Short TSHIRTS") == 0
+
+
+def test_one_machine_both_case_modes(am, golden, oracle, lower_dense):
+    """The reference's own test helper (tests/Data/Text/AhoCorasickSpec.hs:252-261):
+        countMatches caseSensitivity needles haystack =
+          let act = Aho.build $ zip needles (repeat ()); onMatch !n _ = Aho.Step (n + 1)
+          in  Aho.runWithCase caseSensitivity 0 onMatch act haystack
+    `Aho.build` knows nothing of the case mode; ONE machine must serve both."""
+    A = am.automaton
+
+    def count_matches(case_sensitivity, needles, haystack, act=None):
+        act = act or A.build(list(zip(needles, [()] * len(needles))))
+        return A.run_with_case(case_sensitivity, 0, lambda n, _: A.Step(n + 1), act, haystack)
+
+    for v in golden["count"]:
+        assert count_matches(v["cs"], v["needles"], v["haystack"]) == v["expected"], v["src"]
+    rng = np.random.default_rng(77)
+    for it in range(60):
+        needles, hay = needles_haystack(rng, big=60)
+        ln = [am.utf8.lower_utf8(n) for n in needles]
+        hb = hay.encode("utf-8")
+        act = A.build([(n, ()) for n in ln], force_kernel=int(rng.integers(0, 3)) if all(ln) else 0)
+        om = oracle.Machine(ln)
+        for cs in (0, 1, 0):                                   # alternate: the images of both modes live side by side
+            want = as_pairs(om.find_all(hb, cs=cs, lower=lower_dense))
+            assert count_matches(cs, ln, hb, act) == len(want)
+            assert as_pairs(act.find_all(hb, case=cs)) == want
+    # Searcher.setCaseSensitivity flips the flag and keeps needles and automaton (Searcher.hs:142-145)
+    S = am.searcher
+    s0 = S.build(0, ["tshirt", "shirts", "shorts"])
+    s1 = S.set_case_sensitivity(1, s0)
+    assert S.automaton(s1).handle is S.automaton(s0).handle or S.automaton(s1).handle.value == S.automaton(s0).handle.value
+    assert S.contains_any(s0, "Short TSHIRTS") is False and S.contains_any(s1, "Short TSHIRTS") is True
+    assert S.case_sensitivity(s1) == 1 and S.case_sensitivity(S.set_case_sensitivity(0, s1)) == 0
+
+
+def test_two_devices_in_one_process(am, oracle, torch_cuda):
+    """am_options.device: the dynamic shared-memory opt-in, the SM count and the profiling events are per device."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from alfred_margaret_b200 import synth
+    needles = synth.random_needles(200, 42)
+    hay = synth.fill_host(0, 1 << 20, 43)
+    synth.plant_host(hay, 0, 44, needles)
+    want = as_pairs(oracle.Machine(needles).find_all(hay))
+    before = torch_cuda.cuda.current_device()
+    for dev in (0, 1, 0):
+        for kind in (2, 1):
+            m = machine(am, needles, device=dev, force_kernel=kind)
+            assert gpu_pairs(m, hay) == want and m.count_matches(hay) == len(want)
+    assert torch_cuda.cuda.current_device() == before           # the library restores the caller's current device
 
 
 # ---- differential tests on the reference's generator ---------------------------------------------------
@@ -182,6 +234,14 @@ def test_device_resident_and_unaligned(am, oracle, torch_cuda):
         halo = m.info()["halo_bytes"]
         L = am._ffi.lib()
         want = as_pairs(om.find_all(host))
+        # a one-rank communicator: the sharded entry points of the C ABI without a second GPU
+        comm = am.sharded.Comm(0, 1, None)
+        out = torch.empty((len(want) + 8) * 2, dtype=torch.int64, device="cuda")
+        assert comm.count(m, view.data_ptr(), host.size) == (len(want), 0, len(want))
+        assert comm.find_all(m, view.data_ptr(), host.size, out.data_ptr(), len(want) + 8) == (len(want), 0, len(want))
+        assert as_pairs(out[: 2 * len(want)].cpu().numpy().view(am.automaton.MATCH_DTYPE)) == want
+        assert comm.contains_any(m, view.data_ptr(), host.size) is True and comm.allreduce(5, "max") == 5
+        comm.close()
         for n_shards in (2, 3, 8):
             got, total = [], 0
             for r in range(n_shards):

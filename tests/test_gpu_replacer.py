@@ -31,6 +31,56 @@ def test_run_with_limit(am):
         R.build(1, [("", "x")])                                      # empty needle + IgnoreCase: reference diverges
 
 
+def test_set_case_sensitivity_keeps_the_stored_needles(am, oracle, lower_dense):
+    """`setCaseSensitivity` (Replacer.hs:151-153) only flips the searcher's flag: the needles stay as `build` stored them
+    (lowered iff built IgnoreCase, :105-107), the payload lengths stay those of the original needles (:111-113)."""
+    R = am.replacer
+    r = R.set_case_sensitivity(0, R.build(1, [("Foo", "x")]))        # stored needle: "foo"
+    assert R.run(r, "foo Foo") == b"x Foo"                            # (a rebuild from "Foo" would give "foo x")
+    assert R.replacer_case_sensitivity(r) == 0
+    r = R.set_case_sensitivity(1, R.build(0, [("Foo", "x")]))        # stored needle: "Foo" -- never matches lowered text
+    assert R.run(r, "foo Foo FOO") == b"foo Foo FOO"
+    r = R.set_case_sensitivity(1, R.build(0, [("foo", "x")]))
+    assert R.run(r, "foo Foo FOO") == b"x x x"
+    # compose / mapReplacement work on the stored form: no second lowering, lengths kept (:120-141)
+    a, b = R.build(1, [("ÉCLAIR", "bolt")]), R.build(1, [("BOLT", "Blitz")])
+    c = R.compose(a, b)
+    assert R.run(c, "un Éclair") == b"un Blitz"
+    assert R.run(R.map_replacement(lambda rep: rep.upper(), c), "un éclair") == b"un BLITZ"
+    assert R.to_json(c)["replacerSearcher"]["needles"][0] == ["éclair", {"needlePriority": 0, "needleLengthBytes": 7, "needleLengthCodePoints": 6, "needleReplacement": "bolt"}]
+    assert R.run(R.from_json(R.to_json(c)), "un Éclair") == b"un Blitz"
+    rng = np.random.default_rng(5)
+    for it in range(40):                                             # both switches against the oracle on its generator
+        alpha = "abAB"
+        pairs = [("".join(alpha[int(i)] for i in rng.integers(0, 4, size=int(rng.integers(1, 4)))),
+                  "".join(alpha[int(i)] for i in rng.integers(0, 4, size=int(rng.integers(0, 4))))) for _ in range(int(rng.integers(1, 5)))]
+        hay = "".join(alpha[int(i)] for i in rng.integers(0, 4, size=int(rng.integers(0, 40))))
+        lowered = [(n.lower(), rep) for n, rep in pairs]
+        # built IgnoreCase, run CaseSensitive == a CaseSensitive replacer over the lowered needles (ASCII: lengths agree)
+        assert R.run(R.set_case_sensitivity(0, R.build(1, pairs)), hay) == oracle.Replacer(lowered, cs=0, lower=lower_dense).run(hay)
+        # built CaseSensitive over lower-case needles, run IgnoreCase == an IgnoreCase replacer
+        assert R.run(R.set_case_sensitivity(1, R.build(0, lowered)), hay) == oracle.Replacer(lowered, cs=1, lower=lower_dense).run(hay)
+
+
+def test_device_resident_run(am, oracle):
+    import torch
+    R = am.replacer
+    r = R.build(0, [("tshirt", "banana"), ("shirt", "pear")])
+    text = b"sweatshirts and shirttshirts " * 1000
+    dev = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    ptr, n = R.run_dev(r, dev.data_ptr(), len(text))
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    import ctypes
+    cudart = ctypes.CDLL("libcudart.so.12")                       # (already loaded by torch)
+    cudart.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    assert cudart.cudaMemcpy(out.data_ptr(), ptr, n, 3) == 0      # cudaMemcpyDeviceToDevice
+    R.free_dev(ptr)
+    assert bytes(out.cpu().numpy()) == b"sweabananas and pearbananas " * 1000 == R.run(r, text)
+    ptr, n = R.run_dev(R.build(0, [("zzz", "y")]), dev.data_ptr(), len(text))    # nothing to replace: a copy of the input comes back
+    assert n == len(text) and ptr != dev.data_ptr()
+    R.free_dev(ptr)
+
+
 def test_properties_vs_oracle(am, oracle, lower_dense):
     """AhoCorasickSpec.hs:137-163 generators; every result compared with the oracle's Replacer."""
     R = am.replacer
