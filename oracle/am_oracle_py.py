@@ -13,6 +13,22 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libam_oracle.so")
+# AM_ORACLE_NATIVE=1 (bench.py's CPU-timing legs): a -march=native build made on THIS machine, kept
+# apart from the portable one and rebuilt when the CPU model differs from the one it was built on.
+_NATIVE = os.environ.get("AM_ORACLE_NATIVE") == "1"
+if _NATIVE:
+    _LIB_PATH = os.path.join(_HERE, "_build", "native", "libam_oracle.so")
+
+
+def _cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 class U8Slice(C.Structure):
@@ -29,7 +45,14 @@ _lib = None
 
 
 def build_lib(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "am_oracle.c")):
+    stale = not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "am_oracle.c"))
+    if _NATIVE:
+        stamp = _LIB_PATH + ".cpu"
+        if force or stale or not os.path.exists(stamp) or open(stamp).read() != _cpu_model():
+            subprocess.check_call(["make", "-C", _HERE, "native"], stdout=subprocess.DEVNULL)
+            with open(stamp, "w") as f:
+                f.write(_cpu_model())
+    elif force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -37,7 +60,7 @@ def build_lib(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+        if _NATIVE or not os.path.exists(_LIB_PATH):
             build_lib()
         L = C.CDLL(_LIB_PATH)
         L.amo_build.argtypes = [C.POINTER(U8Slice), C.c_size_t, C.POINTER(C.c_void_p)]

@@ -26,7 +26,7 @@ def test_c_host_drives_every_symbol(tmp_path):
     assert got["dev"] == "5,1,5" and got["first"] == "1010:0"                # pos_base is added to every position
     assert got["slice_off"] == "5" and sum(map(int, got["shards"].split("+"))) == 5 and got["any"] == "1" and got["allreduce"] == "41"
     assert got["replace_ic"] == "BAZ BAZ" and got["passes"] == "2"           # foo -> BAR, then bar -> BAZ (AhoCorasickSpec.hs:117-118)
-    assert got["replace_cs"] == "Foo BAZ"
+    assert got["replace_cs"] == "Foo BAR"                                    # CaseSensitive: "BAR" is not "bar"
     assert got["exceeded"] == "1"
     assert got["replace_dev"] == "BAZ BAZ"
     assert got["replace_stored"] == "un bolt"
