@@ -159,7 +159,7 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
   // EMIT on the filter kernel: keys go into per-segment slots of keys_a (first half) + an overflow area (second half)
   ws->emit_segmented = false;
   sa.seg_counts = nullptr; sa.seg_shift = SEG_SHIFT; sa.seg_cap = 0; sa.ovf_base = 0; sa.ovf_cap = 0;
-  sa.lower_ascii = 0; sa.d_nonascii = nullptr;
+  sa.ic_one_pass = 0;
   if (mode == MODE_EMIT && a->kernel_kind == 2 && t.text_len > t.report_begin) {
     const uint64_t num_segs = ((t.text_len - t.report_begin) + (1ull << SEG_SHIFT) - 1) >> SEG_SHIFT;
     uint64_t per = (sa.cap / 2) / num_segs;
@@ -181,53 +181,38 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
   }
   ws->last_kernel = a->kernel_kind;
   if (a->kernel_kind == 2 && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
-    // runLower on the filter kernel: scan a lowered copy of the text (same byte offsets).  Code points whose
-    // lowering changes their UTF-8 length stay as they are in the copy and are matched by the needle variants
-    // the automaton holds for them (am_build.cpp step 1).  Only an automaton that could not take the variants
-    // (ic_copy_exact == false) marks them instead and falls back to the exact per-code-point walk.
-    const bool keep = a->host.ic_copy_exact;
-    // One pass first: if the text is pure ASCII (most logs and English text are), lowering is toLowerAscii on the registers
-    // the text streams through anyway -- no lowered copy, one read of the text.  The kernel flags the first byte above
-    // ASCII and stops; the (few microseconds of) work is thrown away and the text takes the lowered-copy path below.
+    // runLower on the filter kernel.  ONE pass over the original text: the probe and the second level work on folded
+    // bytes (fold8: no `Char.toLower` anywhere near the hot loop), the few survivors are verified on code points lowered
+    // on the fly.  Code points whose lower case has another UTF-8 length are matched by the needle variants the
+    // automaton holds for them (am_build.cpp step 1).  Only an automaton that could not take the variants
+    // (ic_copy_exact == false) scans a lowered COPY of the text in which such code points are marked, and falls back to
+    // the exact per-code-point walk when the text holds one.
     static const bool one_pass_off = []() { const char* v = std::getenv("AM_IC_ONE_PASS"); return v && std::atoi(v) == 0; }();
-    // (needle sets beyond the exact second level produce so many candidates that lowering them one by one costs more than
-    // the lowered copy: measured 10 k needles 845 GB/s in one pass vs 922 GB/s in two, 1 k needles 1 776 vs 1 344)
-    if (keep && a->dev.q == 4 && a->dev.t2_exact && t.text_len >= (1u << 20) && !one_pass_off) {
-      int* d_na = reinterpret_cast<int*>(ws->d_scalars + 24);
-      e = cudaMemsetAsync(d_na, 0, 4, st);
-      sa.lower_ascii = 1; sa.d_nonascii = d_na;
-      if (e == cudaSuccess) e = launch_filter(a->dev, sa, mode, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 24, d_na, 4, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) return cuda_fail(e, "one-pass IgnoreCase scan");
-      if (*reinterpret_cast<int*>(ws->h_scalars + 24) == 0) {
-        if (prof) cudaEventRecord(g_ev1, st);
-        return AM_OK;
-      }
-      sa.lower_ascii = 0; sa.d_nonascii = nullptr;             // not ASCII: start over
-      e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
-      if (e == cudaSuccess && ws->emit_segmented) e = cudaMemsetAsync(ws->seg_counts, 0, (ws->num_segs + 1) * 4, st);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    }
-    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(t.dev_text) & 15);
-    int rc = ws->need_aux(t.text_len + 64, 0);
-    if (rc) return rc;
-    unsigned int* d_exc = reinterpret_cast<unsigned int*>(ws->d_scalars + 16);
-    unsigned int exceptions = 0;
-    e = keep ? cudaSuccess : cudaMemsetAsync(d_exc, 0, 4, st);
-    if (e == cudaSuccess) e = launch_lower(a->dev, sa.text, t.text_len, ws->aux_a + a0, d_exc, keep, st);
-    if (!keep) {
-      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 16, d_exc, 4, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e == cudaSuccess) exceptions = *reinterpret_cast<unsigned int*>(ws->h_scalars + 16);
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "lowering pass");
-    if (exceptions == 0) {
-      sa.text = ws->aux_a + a0;
+    const bool keep = a->host.ic_copy_exact;
+    if (keep && !one_pass_off) {
+      sa.ic_one_pass = 1;
       e = launch_filter(a->dev, sa, mode, st);
     } else {
-      ws->emit_segmented = false; ws->last_kernel = 1;
-      e = launch_walk(a->dev, sa, mode, st);
+      const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(t.dev_text) & 15);
+      int rc = ws->need_aux(t.text_len + 64, 0);
+      if (rc) return rc;
+      unsigned int* d_exc = reinterpret_cast<unsigned int*>(ws->d_scalars + 16);
+      unsigned int exceptions = 0;
+      e = keep ? cudaSuccess : cudaMemsetAsync(d_exc, 0, 4, st);
+      if (e == cudaSuccess) e = launch_lower(a->dev, sa.text, t.text_len, ws->aux_a + a0, d_exc, keep, st);
+      if (!keep) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ws->h_scalars + 16, d_exc, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) exceptions = *reinterpret_cast<unsigned int*>(ws->h_scalars + 16);
+      }
+      if (e != cudaSuccess) return cuda_fail(e, "lowering pass");
+      if (exceptions == 0) {
+        sa.text = ws->aux_a + a0;
+        e = launch_filter(a->dev, sa, mode, st);
+      } else {
+        ws->emit_segmented = false; ws->last_kernel = 1;
+        e = launch_walk(a->dev, sa, mode, st);
+      }
     }
   } else {
     e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
@@ -360,29 +345,34 @@ int lower_utf8_host(const LowerTable& lt, const uint8_t* in, int64_t len, std::v
 }
 
 
-// Host model of filter_kernel's two filter levels (am_filter.cu: fk_probe16 / fk_probe16_s2, fk_phase_a) on the host image.
+// Host model of filter_kernel's two filter levels (am_filter.cu: fk_probe16 / fk_probe16_s2, fk_phase_a) on the host image,
+// with the very cell / hash functions the kernel uses (am_internal.h).  IgnoreCase: `d` is the ORIGINAL text; both levels
+// see it folded (fold8), as in the kernel.
 void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uint32_t align, uint8_t* out_flags) {
-  auto byte_at = [&](uint64_t i) -> uint32_t { return i < n ? d[i] : 0u; };   // the kernel sees arbitrary bytes beyond the text: any value may only ADD candidates
+  const bool ic = H.case_sensitivity == AM_IGNORE_CASE;
+  auto byte_at = [&](uint64_t i) -> uint32_t {   // the kernel sees arbitrary bytes beyond the text: any value may only ADD candidates
+    const uint32_t b = i < n ? d[i] : 0u;
+    return ic ? (fold8(b) & 0xFFu) : b;
+  };
   auto gram4 = [&](uint64_t i) -> uint32_t { return byte_at(i) | byte_at(i + 1) << 8 | byte_at(i + 2) << 16 | byte_at(i + 3) << 24; };
   const bool exact = H.t2_exact != 0;
-  const int copies = filter_copies(H.q, exact);
+  const uint32_t q = H.q;
+  const int copies = filter_copies(q, exact);
   const int rowbits = filter_rowbits(copies);
-  const uint32_t qmask = qgram_mask(H.q);
-  const uint32_t fold = H.case_sensitivity == AM_IGNORE_CASE ? FOLD_MASK : 0u;   // IgnoreCase: `text` is the LOWERED text; the probe folds it
+  const uint32_t qmask = qgram_mask(q);
   for (uint64_t i = 0; i < n; i++) {
     uint32_t level1;
-    if (filter_is_s2(H.q)) {
-      // stride-2 cells: an even virtual position p tests cell A of its own 4-gram, the odd position p + 1 cell B
+    if (filter_is_s2(q)) {
+      // stride-2 cells: an even virtual position p tests cell A of its own q-gram, the odd position p + 1 cell B; the row is
+      // hashed from the q - 1 bytes the two share (for the odd position i these are text[i .. i+q-1), for the even one text[i+1 .. i+q))
       const bool odd = ((align + i) & 1) != 0;
-      const uint64_t p = odd ? i - 1 : i;                                   // the even position of the pair (may be "-1": bytes before the text)
-      const uint32_t x = (odd ? gram4(i) : gram4(i + 1)) | fold;             // the 4-gram at p + 1; its top byte is discarded by the shifted multiplier
-      const uint32_t row = (x * HASH_MUL_S2) >> (32 - rowbits);
-      const uint32_t priv = odd ? byte_at(i + 3) : byte_at(i);              // text[p + 4] resp. text[p]
-      (void)p;
+      const uint64_t b = odd ? i : i + 1;                                      // p + 1
+      const uint32_t row = s2_hash(q, gram4(b), q > 4 ? gram4(b + q - 4) : 0u) >> (32 - rowbits);
+      const uint32_t priv = odd ? byte_at(i + q - 1) : byte_at(i);             // text[p + q] resp. text[p]
       level1 = (H.filter[(size_t)row * copies] >> (31u - (priv & 31u))) & 1u;
     } else {
       uint32_t row, bit;
-      filter_cell((gram4(i) | fold) & qmask, &row, &bit);
+      filter_cell(gram4(i) & qmask, &row, &bit);
       level1 = (H.filter[(size_t)row * copies] >> bit) & 1u;
     }
     const uint32_t g = gram4(i) & qmask;
@@ -393,11 +383,15 @@ void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uin
         const uint32_t* slot = H.filter2.data() + 4 * (size_t)hb;
         uint32_t aux = 0; bool hit = false;
         if (slot[0] == g) { aux = slot[1]; hit = true; } else if (slot[2] == g) { aux = slot[3]; hit = true; }
-        if (hit) { level2 = (aux & T2_AUX_ANY) ? 1u : (byte_at(i + H.q) == (aux & 0xFFu)); break; }
+        if (hit) { level2 = (aux & T2_AUX_ANY) ? 1u : (byte_at(i + q) == (aux & 0xFFu)); break; }
         if (!(slot[3] & T2_AUX_OVERFLOW)) break;
         hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
       }
-    } else if (H.q == 4) {
+    } else if (q > 4) {
+      const uint32_t hi = gram4(i + 4) & (q >= 8 ? 0xFFFFFFFFu : 0xFFFFu);
+      const uint32_t b0 = t2q_bit0(g, hi), b1 = t2q_bit1(g, hi);
+      level2 = (H.filter2[b0 >> 5] >> (b0 & 31)) & (H.filter2[T2Q_WORD1 + (b1 >> 5)] >> (b1 & 31)) & 1u;
+    } else if (q == 4) {
       const uint32_t nb = byte_at(i + 4);
       const uint32_t ba = t2a_bit(g), bb = t2b_bit(g, nb), bc = t2c_bit(g, nb);
       level2 = ((H.filter2[T2A_WORD0 + (ba >> 5)] >> (ba & 31)) | ((H.filter2[T2B_WORD0 + (bb >> 5)] >> (bb & 31)) & (H.filter2[T2C_WORD0 + (bc >> 5)] >> (bc & 31)))) & 1u;
@@ -408,7 +402,6 @@ void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uin
     out_flags[i] = (uint8_t)(level1 | (level2 << 1));
   }
 }
-
 
 }  // namespace am
 

@@ -349,45 +349,65 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   }
 
   // ---- 8. q-gram filter + jump table (filter kernel; not applicable with empty needles) ------------------------
+  // q = the shortest needle's length up to 4; needle sets too large for the exact second level whose shortest needle
+  // has >= 6 (>= 8) bytes take 6- (8-)grams: the bitmaps then answer for more of every needle, and a set of 10^5
+  // needles over a small alphabet -- every 4-gram of which is some needle's prefix -- still filters.
   A->q = 0; A->filter_keys = 0;
   if (A->num_empty == 0 && A->min_len > 0) {
+    const bool ic = cs == AM_IGNORE_CASE;
+    auto keys_at_depth = [&](uint32_t q, std::vector<std::pair<uint64_t, uint32_t>>* keys) {   // (q-gram, state at depth q)
+      keys->clear();
+      for (uint32_t s = 0; s < S; s++) {
+        if (A->depth[s] != q) { if (A->depth[s] > q) break; continue; }
+        uint64_t g = 0; uint32_t t = s;
+        for (uint32_t k = q; k-- > 0;) { g |= (uint64_t)A->in_byte[t] << (8 * k); t = A->parent[t]; }
+        keys->emplace_back(g, s);
+      }
+    };
+    auto folded = [&](uint64_t g, uint32_t q) -> uint64_t { return ic ? (fold8_64(g) & (q >= 8 ? ~0ull : ((1ull << (8 * q)) - 1ull))) : g; };
+    std::vector<std::pair<uint64_t, uint32_t>> keys;
     A->q = std::min<uint32_t>(4, A->min_len);
-    const uint32_t q = A->q;
-    std::vector<std::pair<uint32_t, uint32_t>> keys;  // (q-gram, state at depth q)
-    for (uint32_t s = 0; s < S; s++) {
-      if (A->depth[s] != q) { if (A->depth[s] > q) break; continue; }
-      uint32_t g = 0, t = s;
-      for (uint32_t k = q; k-- > 0;) { g |= (uint32_t)A->in_byte[t] << (8 * k); t = A->parent[t]; }
-      keys.emplace_back(g, s);
+    keys_at_depth(A->q, &keys);
+    {  // the exact second level holds the distinct (folded) q-grams: does it fit?
+      std::unordered_set<uint64_t> distinct;
+      for (auto& kv : keys) distinct.insert(folded(kv.first, A->q));
+      A->t2_exact = distinct.size() <= T2_MAX_EXACT_KEYS;
     }
+    if (!A->t2_exact && FK_S2 && A->min_len >= 6) {
+      A->q = A->min_len >= 8 ? 8 : 6;
+      keys_at_depth(A->q, &keys);
+    }
+    const uint32_t q = A->q;
     A->filter_keys = (uint32_t)keys.size();
     A->filter.assign(FILTER_WORDS, 0);
     uint32_t cap = next_pow2((uint64_t)keys.size() * 2 + 16);
     A->jump.assign(cap, JumpSlot{0, NONE, 0, 0});
     A->tails.clear();
     A->jump_mask = cap - 1;
+    const uint32_t tail_from = std::min<uint32_t>(q, 4);       // the tail of a slot starts at this needle byte
+    const int copies = filter_copies(q, A->t2_exact != 0);
     for (auto& kv : keys) {
-      const bool exact = keys.size() <= T2_MAX_EXACT_KEYS;
-      const int copies = filter_copies(q, exact);
-      const uint32_t gf = cs == AM_IGNORE_CASE ? (kv.first | (FOLD_MASK & qgram_mask(q))) : kv.first;   // IgnoreCase: cells of the folded q-gram
+      const uint64_t gf = folded(kv.first, q);                 // IgnoreCase: cells of the folded q-gram
       if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
         uint32_t ra, ba, rb, bb;
-        filter_cells_s2(gf, filter_rowbits(copies), &ra, &ba, &rb, &bb);
+        filter_cells_s2(gf, q, filter_rowbits(copies), &ra, &ba, &rb, &bb);
         for (int c = 0; c < copies; c++) {
           A->filter[(size_t)ra * copies + c] |= 1u << ba;
           A->filter[(size_t)rb * copies + c] |= 1u << bb;
         }
       } else {
         uint32_t row, bit;
-        filter_cell(gf, &row, &bit);
+        filter_cell((uint32_t)gf, &row, &bit);
         for (int c = 0; c < copies; c++) A->filter[(size_t)row * copies + c] |= 1u << bit;
       }
-      uint32_t i = jump_hash(kv.first) & A->jump_mask;
+      const uint32_t key_lo = (uint32_t)kv.first, key_hi = (uint32_t)(kv.first >> 32);
+      uint32_t i = jump_hash(key_lo, key_hi) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
-      JumpSlot slot{kv.first, tagged(kv.second), 0, 0};
+      JumpSlot slot{key_lo, tagged(kv.second), key_hi, 0};    // not simple: tail_off holds the q-gram's bytes 4 .. q-1
       {  // simple sub-trie?  follow the only child while the state holds no needle end
         uint32_t t = kv.second;
         std::vector<uint8_t> tail;
+        for (uint32_t k = tail_from; k < q; k++) tail.push_back((uint8_t)(kv.first >> (8 * k)));   // the q-gram's own bytes beyond the key
         bool simple = true;
         for (;;) {
           const uint32_t nch = A->child_off[t + 1] - A->child_off[t];
@@ -409,25 +429,33 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       }
       A->jump[i] = slot;
     }
-    // second-level table (shared memory, 32 KiB): exact keys when they fit, else a bitmap
-    A->t2_exact = keys.size() <= T2_MAX_EXACT_KEYS;
+    // second-level table (shared memory, 32 KiB): exact (folded) keys when they fit, else bitmaps
     if (A->t2_exact) {
-      std::vector<uint32_t> sorted_keys;
-      for (auto& kv : keys) sorted_keys.push_back(kv.first);
-      std::sort(sorted_keys.begin(), sorted_keys.end());
+      // key -> aux: the (folded) byte that must follow the q-gram when every needle through it continues with that byte
+      std::unordered_map<uint32_t, uint32_t> aux_of;
+      for (auto& kv : keys) {
+        const uint32_t g = (uint32_t)folded(kv.first, q), s = kv.second;
+        uint32_t aux = T2_AUX_ANY;
+        const bool has_own = A->own_off[s + 1] > A->own_off[s];
+        if (!has_own && A->child_off[s + 1] - A->child_off[s] == 1) {
+          aux = A->child_byte[A->child_off[s]];
+          if (ic) aux = fold8(aux) & 0xFFu;
+        }
+        auto it = aux_of.find(g);
+        if (it == aux_of.end()) aux_of.emplace(g, aux);
+        else if (it->second != aux) it->second = T2_AUX_ANY;   // several exact q-grams fold to this key and disagree
+      }
       uint32_t empty = 0xFFFFFFFFu;  // any value that is not a key (a text q-gram equal to it is rejected later)
-      while (std::binary_search(sorted_keys.begin(), sorted_keys.end(), empty)) empty--;
+      while (aux_of.count(empty)) empty--;
       A->t2_empty_key = empty;
       // buckets of {key0, aux0, key1, aux1}; almost always one probe per lookup: a bucket that would take a
       // third key is flagged "overflow" and only then does a lookup continue in the next bucket
       A->filter2.assign(T2_WORDS, empty);
       for (uint32_t bkt = 0; bkt < (1u << T2_LOG2_BUCKETS); bkt++) { A->filter2[4 * (size_t)bkt + 1] = T2_AUX_ANY; A->filter2[4 * (size_t)bkt + 3] = T2_AUX_ANY; }
-      for (auto& kv : keys) {
-        const uint32_t g = kv.first, s = kv.second;
-        // aux: the byte that must follow the q-gram, when every needle through this state continues with it
-        uint32_t aux = T2_AUX_ANY;
-        const bool has_own = A->own_off[s + 1] > A->own_off[s];
-        if (!has_own && A->child_off[s + 1] - A->child_off[s] == 1) aux = A->child_byte[A->child_off[s]];
+      std::vector<std::pair<uint32_t, uint32_t>> sorted_aux(aux_of.begin(), aux_of.end());
+      std::sort(sorted_aux.begin(), sorted_aux.end());        // deterministic table layout
+      for (auto& ga : sorted_aux) {
+        const uint32_t g = ga.first, aux = ga.second;
         uint32_t hb = t2_bucket(g);
         for (;;) {
           uint32_t* slot = A->filter2.data() + 4 * (size_t)hb;
@@ -441,12 +469,19 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       A->filter2.assign(T2_WORDS, 0);
       auto set_bit = [&](uint32_t word0, uint32_t bit) { A->filter2[word0 + (bit >> 5)] |= 1u << (bit & 31); };
       for (auto& kv : keys) {
-        if (q != 4) { set_bit(0, filter2_bit(kv.first)); continue; }
-        const uint32_t g = kv.first, s = kv.second;        // q = 4: closed 4-grams + the 5-grams of the needles that go on
+        const uint64_t gf = folded(kv.first, q);
+        if (q < 4) { set_bit(0, filter2_bit((uint32_t)gf)); continue; }
+        if (q > 4) {                                           // Bloom filter over the whole q-gram, one bit per half
+          set_bit(0, t2q_bit0((uint32_t)gf, (uint32_t)(gf >> 32)));
+          set_bit(T2Q_WORD1, t2q_bit1((uint32_t)gf, (uint32_t)(gf >> 32)));
+          continue;
+        }
+        const uint32_t g = (uint32_t)gf, s = kv.second;       // q = 4: closed 4-grams + the 5-grams of the needles that go on
         if (A->own_off[s + 1] > A->own_off[s]) set_bit(T2A_WORD0, t2a_bit(g));
         for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) {
-          set_bit(T2B_WORD0, t2b_bit(g, A->child_byte[c]));
-          set_bit(T2C_WORD0, t2c_bit(g, A->child_byte[c]));
+          const uint32_t nb = ic ? (fold8(A->child_byte[c]) & 0xFFu) : A->child_byte[c];
+          set_bit(T2B_WORD0, t2b_bit(g, nb));
+          set_bit(T2C_WORD0, t2c_bit(g, nb));
         }
       }
     }

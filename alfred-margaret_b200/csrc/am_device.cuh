@@ -49,9 +49,9 @@ struct ScanArgs {
   // filter kernel, EMIT: keys go into per-segment slots of d_keys (segment = 2^seg_shift bytes of end positions, seg_cap
   // slots each, counters in seg_counts); keys of a full segment go to d_keys[ovf_base ..) and are counted in d_count
   uint32_t* seg_counts; uint32_t seg_shift, seg_cap; uint64_t ovf_base, ovf_cap;
-  // filter kernel, IgnoreCase in one pass: lower the ASCII letters while the text streams through the registers; a byte
-  // >= 0x80 anywhere sets *d_nonascii and ends the launch (the host then takes the lowered-copy path instead)
-  uint32_t lower_ascii; int* d_nonascii;
+  // filter kernel, IgnoreCase: 1 = `text` is the ORIGINAL text (one pass: folded probe, survivors lowered on the fly);
+  // 0 = `text` is a lowered copy
+  uint32_t ic_one_pass;
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)

@@ -24,6 +24,12 @@
 
 namespace am {
 
+#if defined(__CUDACC__)
+#define AM_HD_DECL __host__ __device__ __forceinline__
+#else
+#define AM_HD_DECL inline
+#endif
+
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t OUT_FLAG = 0x80000000u;   // stored state id: its output chain (own ++ inherited) is non-empty
 constexpr uint32_t OWN_FLAG = 0x40000000u;   // stored state id: some needle ends exactly at this state
@@ -50,6 +56,9 @@ struct EdgeSlot { uint32_t key_lo, key_hi, child, pad; };   // key = state << 8 
 // `tail_off` = offset of the tail bytes in HostAutomaton::tails (4-byte aligned), and `state` = the LEAF's state --
 // or, with JUMP_SINGLE (one needle ends there), directly that needle's rank.  The survivor check is then one
 // byte-wise comparison whose loads are all independent, instead of one dependent hashed edge lookup per byte.
+// For q > 4 the key is the q-gram's first four bytes and the table is hashed by all q: the bytes 4 .. q - 1 are checked
+// against the head of the tail (the tail of a slot starts at needle byte min(q, 4)) or, for a slot that is not simple,
+// against `tail_off`, which then holds those bytes; a slot that fails this check is another q-gram's: probing goes on.
 struct JumpSlot { uint32_t key, state, tail_off, meta; };
 constexpr uint32_t JUMP_SIMPLE = 0x80000000u, JUMP_SINGLE = 0x40000000u, JUMP_TAIL_MASK = 0xFFFFu;
 
@@ -79,7 +88,7 @@ struct HostAutomaton {
   uint32_t max_len_cps = 0;
   uint32_t num_empty = 0;              // empty needles (reported after every successful transition, A.4)
   bool ic_copy_exact = true;           // IgnoreCase: needle variants cover every length-changing pre-image (no fallback needed)
-  uint32_t q = 0;                      // filter q-gram length, 0 => filter kernel not applicable
+  uint32_t q = 0;                      // filter q-gram length (1..4, 6 or 8), 0 => filter kernel not applicable
   uint32_t rank_bits = 1;
   uint64_t halo_bytes = 0;             // bytes a shard needs before its report range
 
@@ -112,11 +121,6 @@ struct HostAutomaton {
 int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_lower_table* lower,
                          HostAutomaton* out, std::string* err);
 
-#if defined(__CUDACC__)
-#define AM_HD_DECL __host__ __device__ __forceinline__
-#else
-#define AM_HD_DECL inline
-#endif
 inline uint32_t qgram_mask(uint32_t q) { return q >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q)) - 1u); }
 // Build-time variants of the filter kernel (A/B-tested on the GPU):
 //   FK_S2         stride-2 probe for q = 4: ONE bitmap word answers "does a needle start at p" and "does a needle
@@ -158,7 +162,7 @@ constexpr int filter_rowbits(int copies) { return copies == 32 ? 10 : copies == 
 constexpr int FILTER_ROWBITS_S1 = filter_rowbits(FK_COPIES_S1);
 static_assert((1 << filter_rowbits(FK_COPIES_S2)) * FK_COPIES_S2 == FILTER_WORDS && (1 << filter_rowbits(FK_COPIES_S2_BIG)) * FK_COPIES_S2_BIG == FILTER_WORDS &&
               (1 << FILTER_ROWBITS_S1) * FK_COPIES_S1 == FILTER_WORDS, "filter geometry");
-inline bool filter_is_s2(uint32_t q) { return FK_S2 && q == 4; }
+inline bool filter_is_s2(uint32_t q) { return FK_S2 && q >= 4; }
 // Copies of the bitmap for an automaton: `exact` = its q-grams fit the exact second-level table (t2_exact).
 constexpr int filter_copies_s2(bool exact) { return exact ? FK_COPIES_S2 : FK_COPIES_S2_BIG; }
 inline int filter_copies(uint32_t q, bool exact) { return filter_is_s2(q) ? filter_copies_s2(exact) : FK_COPIES_S1; }
@@ -174,15 +178,33 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
 //   cell A (needle starts at the even position p):      row of (n1, n2, n3), bit chosen by n0
 //   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
 constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
-// IgnoreCase automata: the filter bitmap holds the cells of the case-FOLDED q-grams (every byte | 0x20) and the kernel
-// folds the text the same way before it probes; the second level and the verification work on exact (lowered) bytes.
-constexpr uint32_t FOLD_MASK = 0x20202020u;
-inline void filter_cells_s2(uint32_t g, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
-  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - rowbits);
-  *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31
-  *row_b = (g * HASH_MUL_S2) >> (32 - rowbits);
-  *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
+// Longer q-grams (needle sets whose shortest needle has >= 6 / >= 8 bytes and that are too large for the exact second
+// level): the row is hashed from the q - 1 bytes the two q-grams at p and p + 1 share, text[p+1 .. p+q), as
+//   y = X(p+1) * HASH_MUL + X(p+q-3) * (HASH_MUL_B << 8)
+// where X(i) is the 4-gram at i: the shifted multiplier drops the top byte of the second 4-gram, text[p+q], which is the
+// private byte of cell B.  X(p+q-3) is the first 4-gram of the next pair (q = 6) or of the pair after that (q = 8), so
+// the longer q-gram costs one more IMAD per pair.  Must match fk_probe16_s2.
+constexpr uint32_t HASH_MUL_B = 0xCC9E2D51u;
+constexpr uint32_t HASH_MUL_BS = HASH_MUL_B << 8;
+AM_HD_DECL uint32_t s2_hash(uint32_t q, uint32_t x1, uint32_t xk) { return q == 4 ? x1 * HASH_MUL_S2 : x1 * HASH_MUL + xk * HASH_MUL_BS; }
+// Stride-2 cells of a needle whose first q bytes are g (byte i at bits 8 i; q = 4, 6, 8):
+//   cell A (needle starts at the even position p):      row of bytes 1 .. q-1, bit chosen by byte 0
+//   cell B (needle starts at the odd position p + 1):   row of bytes 0 .. q-2, bit chosen by byte q-1
+inline void filter_cells_s2(uint64_t g, uint32_t q, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
+  const uint64_t sa = g >> 8;
+  *row_a = s2_hash(q, (uint32_t)sa, (uint32_t)(sa >> (8 * (q - 4)))) >> (32 - rowbits);
+  *bit_a = 31u - (uint32_t)(g & 31u);                        // the kernel rotates left by text[p] and tests bit 31
+  *row_b = s2_hash(q, (uint32_t)g, (uint32_t)(g >> (8 * (q - 4)))) >> (32 - rowbits);
+  *bit_b = 31u - (uint32_t)((g >> (8 * (q - 1))) & 31u);    // ... by text[p + q]
 }
+// IgnoreCase automata: the filter works on FOLDED bytes -- an ASCII byte | 0x20 (a letter and its upper case fold to the
+// same byte), a byte >= 0x80 | 0x3F (continuation bytes fold to 0xBF, lead bytes to 0xFF: `Char.toLower` may change any
+// byte of a multi-byte code point, but never which bytes are lead bytes as long as it keeps the UTF-8 length; code points
+// whose lower case has another length are kept and matched by needle variants).  Bitmap cells and the second level hold
+// folded q-grams and the kernel folds the text the same way before it probes, so the probe never sees `Char.toLower`:
+// folding can add candidates, never lose one.  The survivors are verified on exactly lowered code points.
+AM_HD_DECL uint32_t fold8(uint32_t w) { return w | 0x20202020u | (((w >> 7) & 0x01010101u) * 0x3Fu); }
+AM_HD_DECL uint64_t fold8_64(uint64_t w) { return (uint64_t)fold8((uint32_t)w) | ((uint64_t)fold8((uint32_t)(w >> 32)) << 32); }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
 // Second level for q = 4 needle sets too large for the exact table (T2_MAX_EXACT_KEYS): three bitmaps in the 32 KiB.
 //   T2A (64 Ki bits):  4-grams that END a needle (a needle of exactly four bytes);
@@ -193,6 +215,13 @@ constexpr int T2A_LOG2 = 16, T2B_LOG2 = 17, T2C_LOG2 = 16;
 constexpr uint32_t T2A_WORD0 = 0, T2B_WORD0 = (1u << T2A_LOG2) / 32, T2C_WORD0 = T2B_WORD0 + (1u << T2B_LOG2) / 32;
 static_assert(T2C_WORD0 + (1u << T2C_LOG2) / 32 == (uint32_t)T2_WORDS, "T2 bitmap geometry");
 constexpr uint32_t HASH_MUL3 = 0xC2B2AE35u;
+// Second level for q > 4: a partitioned Bloom filter over the whole q-gram (lo = bytes 0..3, hi = bytes 4..q-1), one bit in
+// each half of the 32 KiB (2 x 128 Ki bits).  Must match fk_phase_a.
+constexpr int T2Q_LOG2 = 17;
+constexpr uint32_t T2Q_WORD1 = (1u << T2Q_LOG2) / 32;
+static_assert(2 * T2Q_WORD1 == (uint32_t)T2_WORDS, "T2Q geometry");
+AM_HD_DECL uint32_t t2q_bit0(uint32_t lo, uint32_t hi) { return ((lo * HASH_MUL2) ^ (hi * HASH_MUL)) >> (32 - T2Q_LOG2); }
+AM_HD_DECL uint32_t t2q_bit1(uint32_t lo, uint32_t hi) { return ((lo ^ (hi * 0x01000193u) ^ (hi >> 15)) * HASH_MUL3) >> (32 - T2Q_LOG2); }
 AM_HD_DECL uint32_t t2a_bit(uint32_t g4) { return (g4 * HASH_MUL2) >> (32 - T2A_LOG2); }
 AM_HD_DECL uint32_t t2b_bit(uint32_t g4, uint32_t b4) { return ((g4 * HASH_MUL2) ^ (b4 * HASH_MUL)) >> (32 - T2B_LOG2); }
 AM_HD_DECL uint32_t t2c_bit(uint32_t g4, uint32_t b4) { return ((g4 ^ (b4 * 0x01000193u)) * HASH_MUL3) >> (32 - T2C_LOG2); }
@@ -203,7 +232,7 @@ inline uint32_t t2_bucket(uint32_t g) { return (g * HASH_MUL2) >> (32 - T2_LOG2_
 #else
 #define AM_HD inline
 #endif
-AM_HD uint32_t jump_hash(uint32_t g) { uint32_t h = g * HASH_MUL2; return h ^ (h >> 15); }
+AM_HD uint32_t jump_hash(uint32_t g, uint32_t g_hi = 0) { uint32_t h = g * HASH_MUL2 + g_hi * HASH_MUL3; return h ^ (h >> 15); }
 AM_HD uint32_t edge_hash(uint32_t state, uint32_t byte) {
   uint32_t h = state * HASH_MUL + byte * 0x01000193u; return h ^ (h >> 15);
 }

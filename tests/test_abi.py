@@ -174,21 +174,23 @@ def test_filter_has_no_false_negatives(oracle):
         ("shared prefixes, duplicates", [b"abca", b"abcab", b"abcabc", b"bcab", b"abca", b"cabcabcab", b"aaaa", b"aaaab"], b"abc"),
         ("bytes with equal low 5 bits, UTF-8", ["aAb!", "!bAa", "Aa!b1", "åbcå", "💩ab", "ab💩", "ßßab"], "aA!b1åß💩"),
     ]
+    cases.append(("q = 6: Bloom second level", synth.random_needles(5000, 47, 6, 12), synth.AZ))
+    cases.append(("q = 8", synth.random_needles(4000, 48, 8, 16), synth.AZ))
+    cases.append(("q = 6, C5-like density", synth.random_needles(30000, 49, 6, 16), synth.AZ))
     cases.append(("IgnoreCase: folded cells", synth.random_needles(1000, 46) + [b"a@b`", b"[x]{y}", b"  ab", b"12ab"], "IC"))
+    cases.append(("IgnoreCase: folded cells, q = 6", synth.random_needles(3000, 50, 6, 12), "IC"))
     for name, needles, alpha in cases:
         nb = [n if isinstance(n, bytes) else n.encode("utf-8") for n in needles]
         if alpha == "IC":
-            # the probe sees every byte | 0x20 (upper and lower case fold together); the second level sees the LOWERED text
-            from alfred_margaret_b200 import utf8
+            # the model is handed the ORIGINAL text; both filter levels see it folded (every ASCII byte | 0x20), never lowered
             raw = synth.fill_host(0, 1 << 18, 11, synth.AZ + synth.AZ.upper() + b" @`[]{}12")
             synth.plant_host(raw, 0, 12, [x.upper() for x in nb], block=512)
-            hay = np.frombuffer(utf8.lower_utf8(raw.tobytes()), dtype=np.uint8).copy()
             m = automaton.AcMachine([(n, i) for i, n in enumerate(nb)], case_sensitivity=1, device=-2, force_kernel=2)
-            want = oracle.Machine(nb).find_all(hay, cap=1 << 22)   # (lowered text, lowered needles: plain matching)
+            want = oracle.Machine(nb).find_all(raw, cs=1, cap=1 << 22)   # (ASCII text: no table needed)
             assert len(want) > 100 and m.info()["kernel_kind"] == 2
             starts = np.unique(want["pos"] - np.array([len(nb[v]) for v in want["value"]], dtype=np.int64))
             for align in (0, 1):
-                flags = m.host_filter_flags(hay, align)
+                flags = m.host_filter_flags(raw, align)
                 assert starts[(flags[starts] & 3) != 3].size == 0, (name, align)
                 assert float((flags & 1).mean()) < 0.05
             continue
@@ -201,6 +203,9 @@ def test_filter_has_no_false_negatives(oracle):
         assert m.info()["kernel_kind"] == 2, name
         want = oracle.Machine(nb).find_all(hay, cap=1 << 22)
         assert len(want) > 100, name
+        if name.startswith("q = 6, C5"):                        # the long q-gram keeps a large set selective (a 4-gram bitmap would pass ~7 %)
+            f0 = m.host_filter_flags(hay, 0)
+            assert float((f0 & 1).mean()) < 0.08 and float(((f0 & 3) == 3).mean()) < 0.01
         starts = np.unique(want["pos"] - np.array([len(nb[v]) for v in want["value"]], dtype=np.int64))
         for align in (0, 1):
             flags = m.host_filter_flags(hay, align)

@@ -441,10 +441,42 @@ def test_large_positions_and_kernel_choice(am, oracle, torch_cuda):
     assert machine(am, synth.random_needles(1000, 42)).info()["kernel_kind"] == 2
     assert machine(am, synth.random_needles(40000, 43, 6, 12)).info()["kernel_kind"] == 2
     big = machine(am, synth.random_needles(100000, 43, 6, 12))
-    assert big.info()["kernel_kind"] == 1                      # too many distinct q-grams for the shared-memory bitmap
-    forced = machine(am, synth.random_needles(100000, 43, 6, 12), force_kernel=2)
+    assert big.info()["kernel_kind"] == 2                      # shortest needle 6 bytes: 6-grams keep the filter selective
+    walk = machine(am, synth.random_needles(100000, 43, 6, 12), force_kernel=1)
     hay = synth.fill_host(0, 1 << 20, 44)
-    assert as_pairs(forced.find_all(hay)) == as_pairs(big.find_all(hay))
+    synth.plant_host(hay, 0, 45, synth.random_needles(100000, 43, 6, 12))
+    assert len(big.find_all(hay)) > 200 and as_pairs(walk.find_all(hay)) == as_pairs(big.find_all(hay))
+    four = machine(am, synth.random_needles(100000, 46, 4, 12))
+    assert four.info()["kernel_kind"] == 1                     # 4-byte needles force 4-grams: too many for the shared-memory bitmap
+
+
+@pytest.mark.parametrize("lens", [(6, 16), (8, 16), (6, 7), (8, 8)])
+def test_long_qgram_filter(am, oracle, torch_cuda, lens):
+    """Needle sets beyond the exact second level whose shortest needle has >= 6 (>= 8) bytes take 6- (8-)gram stride-2 cells
+    and a Bloom second level; the jump table is keyed by the whole q-gram.  Both kernels against the oracle, at every
+    alignment of the device text, with prefix-sharing needles (same first four bytes, different q-gram) and duplicates."""
+    torch = torch_cuda
+    from alfred_margaret_b200 import synth
+    needles = synth.random_needles(6000, 91 + lens[0], lens[0], lens[1], b"abcdefgh")
+    stem = needles[0][:4]
+    needles += [stem + b"abcd" + b"x" * (lens[0] - 4), stem + b"abce" + b"x" * (lens[0] - 4), stem + b"bbbbbbbb", needles[1], needles[2] + b"zz"]
+    n = (2 << 20) + 77
+    host = synth.fill_host(0, n, 7, b"abcdefgh")
+    synth.plant_host(host, 0, 8, needles, block=256)
+    want = oracle.Machine(needles).find_all(host, threads=4, cap=1 << 22)
+    assert len(want) > 8000
+    m = machine(am, needles)
+    assert m.info()["kernel_kind"] == 2
+    dev = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    for off in (0, 1, 2, 7, 16):
+        view = dev[off:off + n]
+        view.copy_(torch.from_numpy(host))
+        assert m.count_matches_dev(view.data_ptr(), n) == len(want)
+        out = torch.empty(2 * (len(want) + 1), dtype=torch.int64, device="cuda")
+        k = m.find_all_dev(view.data_ptr(), n, out.data_ptr(), len(want) + 1)
+        rec = out[: 2 * k].cpu().numpy().view(am.automaton.MATCH_DTYPE)
+        assert k == len(want) and np.array_equal(rec["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(rec["needle_id"].astype(np.int64), want["value"]), off
+    assert m.contains_any(host) is True and m.contains_any(b"zzzzzzzzzzzzzzzzzzzz" * 100) is False
 
 
 def test_launch_span_boundary(am, oracle, torch_cuda):
@@ -558,10 +590,11 @@ def test_host_scans_pipelined_in_chunks(am, oracle):
     assert mi.count_matches(up) == len(want) and mi.contains_any(up) is True and m.count_matches(up) == 0
 
 
-def test_ignore_case_one_pass_on_ascii_text(am, oracle, lower_dense, torch_cuda):
-    """runLower on the filter kernel: a text of >= 1 MiB is first scanned in ONE pass that lowers ASCII letters in the
-    registers (no lowered copy); the first byte above ASCII anywhere -- here: only in the very last granule -- makes the
-    kernel give up and the text takes the lowered-copy path.  Both must equal the oracle's runLower."""
+def test_ignore_case_one_pass_any_text(am, oracle, lower_dense, torch_cuda):
+    """runLower on the filter kernel is ONE pass over the original text, whatever it holds: the probe sees folded bytes,
+    the survivors are lowered code point by code point.  ASCII text, text with single code points above ASCII at awkward
+    places, and a text dense in multi-byte code points whose lower case changes the lead byte (Я), a continuation byte
+    (É, Ω) or the UTF-8 length (K, ẞ: matched by needle variants) must all equal the oracle's runLower."""
     from alfred_margaret_b200 import synth
     needles = synth.random_needles(1000, 42)
     n = (4 << 20) + 123
@@ -582,3 +615,25 @@ def test_ignore_case_one_pass_on_ascii_text(am, oracle, lower_dense, torch_cuda)
         assert m.count_matches(h) == len(want) and m.contains_any(h) is True
         dev = torch_cuda.from_numpy(h).cuda()                      # device-resident, unaligned
         assert m.count_matches_dev(dev.data_ptr() + 3, n - 3) == len(om.find_all(h[3:], cs=1, lower=lower_dense, cap=1 << 20))
+    # dense multi-byte text; needles with non-ASCII code points; exact and Bloom second levels (1 200 / 6 000 needles)
+    rng = np.random.default_rng(9)
+    for count, lo_len in ((1200, 4), (6000, 4), (6000, 6)):
+        pool = list("abcdefghikst") * 2 + list("åßяéωǳ")
+        nd = sorted({"".join(rng.choice(pool, size=int(rng.integers(lo_len, 11)))) for _ in range(count)})
+        nb = [x.encode("utf-8") for x in nd]
+        cps = list("abcdefghikst ") * 2 + list("ABCDEFGHIKST") + list("åßяéωǳ") + list("ÅẞЯÉΩǲǱKİ") + ["𝄞", "€"]
+        up = {"å": "Å", "я": "Я", "é": "É", "ω": "Ω", "ǳ": "ǲ", "k": "K", "i": "İ", "ß": "ẞ"}
+        parts = []
+        for _ in range(1500):                                  # random text with a randomly re-cased needle every ~270 symbols
+            parts.append("".join(rng.choice(cps, size=int(rng.integers(200, 340)))))
+            w = nd[int(rng.integers(0, len(nd)))]
+            parts.append("".join((up.get(c, c.upper()) if rng.random() < 0.5 else c) for c in w))
+        text = "".join(parts)
+        hb = np.frombuffer(text.encode("utf-8"), dtype=np.uint8).copy()
+        want = oracle.Machine(nb).find_all(hb, cs=1, lower=lower_dense, cap=1 << 22)
+        assert len(want) > 300, (count, len(want))
+        for force in (0, 1):
+            mm = machine(am, nb, cs=1, force_kernel=force)
+            got = mm.find_all(hb)
+            assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (count, lo_len, force)
+            assert mm.count_matches(hb) == len(want)
