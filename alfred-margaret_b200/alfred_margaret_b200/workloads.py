@@ -59,10 +59,11 @@ def c3_needles(n: int = 10000):
 
 
 def c3_unit(needles, size: int = C3_UNIT, seed: int = 53) -> np.ndarray:
-    """`size` bytes of mixed-case UTF-8: 70 % ASCII letters of either case, 10 % space / punctuation, 15 % two-byte code
-    points (Latin-1, Cyrillic, Greek, the DZ digraphs), 4 % three-byte (incl. K U+212A, Å U+212B, ẞ: their lower case has
-    another UTF-8 length), 1 % four-byte; about one randomly re-cased needle per 3 500 symbols.  Ends on a code point
-    boundary (padded with spaces), so units can be laid back to back."""
+    """`size` bytes of mixed-case UTF-8: 70 % ASCII letters of either case, 10 % space / punctuation,
+    15 % two-byte code points (the letters of the Latin-1 supplement and of the Cyrillic block in either case, plus ω Ω and the
+    DZ digraphs so that every needle letter occurs), 4 % three-byte (incl. K U+212A, Å U+212B, ẞ, whose lower case has another
+    UTF-8 length; ⱥ; general punctuation), 1 % four-byte; about one randomly re-cased needle per 3 500 symbols.  Ends on a
+    code point boundary (padded with spaces), so units can be laid back to back."""
     rng = np.random.default_rng(seed)
     ascii_l = "abcdefghijklmnopqrstuvwxyz"
     syms, wts = [], []
@@ -70,7 +71,10 @@ def c3_unit(needles, size: int = C3_UNIT, seed: int = 53) -> np.ndarray:
     def add(chars, total):
         for c in chars:
             syms.append(c.encode("utf-8")); wts.append(total / len(chars))
-    add(ascii_l + ascii_l.upper(), 0.70); add(" .,;-", 0.10); add("éÉöÖßåÅяЯωΩǳǲǱ", 0.15); add("ẞKÅⱥ€", 0.04); add("𝄞💩", 0.01)
+    latin1 = "".join(chr(c) for c in range(0xC0, 0x100) if c not in (0xD7, 0xF7))
+    cyrillic = "".join(chr(c) for c in range(0x410, 0x450))
+    add(ascii_l + ascii_l.upper(), 0.70); add(" .,;-", 0.10); add(latin1 + cyrillic + "\u03c9\u03a9\u01f3\u01f2\u01f1", 0.15)
+    add("\u1e9e\u212a\u212b\u2c65\u20ac\u2013\u2026\u201c\u201d", 0.04); add("\U0001d11e\U0001f4a9", 0.01)
     plants = []
     for _ in range(512):
         nd = needles[int(rng.integers(0, len(needles)))].decode("utf-8")

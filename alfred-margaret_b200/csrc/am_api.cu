@@ -63,7 +63,7 @@ static int upload(Image* a, const std::vector<T>& v, const T** out) {
 }
 
 Workspace::~Workspace() {
-  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases, (void*)seen_bits})
+  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases, (void*)seen_bits, (void*)surv})
     if (p) cudaFree(p);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -103,6 +103,7 @@ int Workspace::need_segs(uint64_t n) {
   return ws_grow((void**)&seg_bases, &seg_bases_bytes, n * 8 + 16, "segment bases");
 }
 
+int Workspace::need_surv(uint64_t entries) { return ws_grow((void**)&surv, &surv_bytes, entries * 16, "survivor list"); }
 int Workspace::need_seen(uint64_t bits) { return ws_grow((void**)&seen_bits, &seen_bytes, (bits + 31) / 32 * 4 + 16, "needle bit set"); }
 
 Image::~Image() {
@@ -156,11 +157,26 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
   sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q, a->dev.t2_exact != 0);
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  // filter scan: the survivor list between filter_kernel and verify_kernel.  1 / 256 of the positions to begin with (C2: 1 / 2000
+  // survive); a scan that produces more is repeated with the list grown to what it asked for (scan_overflowed).
+  sa.surv = nullptr; sa.surv_count = reinterpret_cast<unsigned long long*>(ws->d_scalars + 48); sa.surv_cap = 0; sa.any_mode = mode == MODE_ANY;
+  ws->last_span = t.text_len - std::min(t.report_begin, t.text_len);
+  Image* am = const_cast<Image*>(a);
+  const unsigned scan_no = am->scans.fetch_add(1, std::memory_order_relaxed);
+  const bool use_filter = a->kernel_kind == 2 && !ws->force_walk && !(am->walk_streak.load(std::memory_order_relaxed) >= 2 && (scan_no & 7u) != 0);
+  ws->force_walk = false;
+  if (use_filter) {
+    const uint64_t span = ws->last_span;
+    int rc = ws->need_surv(std::max<uint64_t>(1u << 16, span / 256));
+    if (rc) return rc;
+    sa.surv = ws->surv; sa.surv_cap = ws->surv_bytes / 16;
+    if ((e = cudaMemsetAsync(ws->d_scalars + 48, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  }
   // EMIT on the filter kernel: keys go into per-segment slots of keys_a (first half) + an overflow area (second half)
   ws->emit_segmented = false;
   sa.seg_counts = nullptr; sa.seg_shift = SEG_SHIFT; sa.seg_cap = 0; sa.ovf_base = 0; sa.ovf_cap = 0;
   sa.ic_one_pass = 0;
-  if (mode == MODE_EMIT && a->kernel_kind == 2 && t.text_len > t.report_begin) {
+  if (mode == MODE_EMIT && use_filter && t.text_len > t.report_begin) {
     const uint64_t num_segs = ((t.text_len - t.report_begin) + (1ull << SEG_SHIFT) - 1) >> SEG_SHIFT;
     uint64_t per = (sa.cap / 2) / num_segs;
     uint32_t seg_cap = 0;
@@ -179,17 +195,18 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
     g_ev0 = ws->ev0; g_ev1 = ws->ev1; g_ev_device = a->device;
     cudaEventRecord(g_ev0, st);
   }
-  ws->last_kernel = a->kernel_kind;
-  if (a->kernel_kind == 2 && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
+  ws->last_kernel = use_filter ? 2 : 1;
+  if (use_filter && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
     // runLower on the filter kernel.  ONE pass over the original text: the probe and the second level work on folded
-    // bytes (fold8: no `Char.toLower` anywhere near the hot loop), the few survivors are verified on code points lowered
+    // bytes (every byte | 0x20; the cells hold every case variant of the needles' first code points: no `Char.toLower`
+    // anywhere near the hot loop), the few survivors are verified on code points lowered
     // on the fly.  Code points whose lower case has another UTF-8 length are matched by the needle variants the
     // automaton holds for them (am_build.cpp step 1).  Only an automaton that could not take the variants
     // (ic_copy_exact == false) scans a lowered COPY of the text in which such code points are marked, and falls back to
     // the exact per-code-point walk when the text holds one.
     static const bool one_pass_off = []() { const char* v = std::getenv("AM_IC_ONE_PASS"); return v && std::atoi(v) == 0; }();
     const bool keep = a->host.ic_copy_exact;
-    if (keep && !one_pass_off) {
+    if (keep && a->host.ic_fold_ok && !one_pass_off) {
       sa.ic_one_pass = 1;
       e = launch_filter(a->dev, sa, mode, st);
     } else {
@@ -215,14 +232,41 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
       }
     }
   } else {
-    e = a->kernel_kind == 2 ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
+    e = use_filter ? launch_filter(a->dev, sa, mode, st) : launch_walk(a->dev, sa, mode, st);
   }
   if (prof) cudaEventRecord(g_ev1, st);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return AM_OK;
 }
 
+// Scan in COUNT / ANY mode and read the counters back; a scan whose survivor list was too short is repeated.
+int scan_sync(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st);
+
+// After read_scalars: did the last filter scan produce more survivors than its list holds?  Then its results are incomplete:
+// grow the list to what the scan asked for and tell the caller to repeat it.
+int scan_overflowed(Workspace* ws, bool* again) {
+  *again = false;
+  const uint64_t want = *reinterpret_cast<const uint64_t*>(ws->h_scalars + 48);
+  if (ws->surv == nullptr || want <= ws->surv_bytes / 16) return AM_OK;
+  *again = true;
+  return ws->need_surv(want + want / 4);
+}
+
+int scan_sync(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st) {
+  for (int attempt = 0;; attempt++) {
+    int rc = launch_scan(a, ws, t, mode, st);
+    if (!rc) rc = read_scalars(ws, st);
+    if (rc) return rc;
+    if (mode == MODE_ANY && *reinterpret_cast<int*>(ws->h_scalars + 8) != 0) return AM_OK;   // a match is a match, however many survivors went unlisted
+    bool again = false;
+    if ((rc = scan_overflowed(ws, &again))) return rc;
+    if (!again) return AM_OK;
+    if (attempt >= 3) return fail(AM_E_INTERNAL, "survivor count kept growing");
+  }
+}
+
 int read_scalars(Workspace* ws, cudaStream_t st, size_t bytes) {
+  if (bytes < 64) bytes = 64;
   cudaError_t e = cudaMemcpyAsync(ws->h_scalars, ws->d_scalars, bytes, cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(scalars)");
   e = cudaStreamSynchronize(st);
@@ -263,9 +307,17 @@ int emit_enqueue(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream
 int emit_finish(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked) {
   if (unpacked) *unpacked = false;
   const int end_bit = std::min(64, bitlen(t.text_len + t.pos_base) + (int)a->host.rank_bits);
-  int rc;
+  int rc = AM_OK;
   for (int attempt = 0;; attempt++) {
     const uint64_t cap = ws->keys_a_bytes / 8;
+    bool again = false;
+    if ((rc = scan_overflowed(ws, &again))) return rc;
+    if (again) {                                   // the survivor list was too short: the keys are incomplete; scan again (the list has grown)
+      if (attempt >= 3) return fail(AM_E_INTERNAL, "survivor count kept growing");
+      if ((rc = emit_enqueue(a, ws, t, st, matches, matches_cap))) return rc;
+      if ((rc = read_scalars(ws, st))) return rc;
+      continue;
+    }
     if (ws->emit_segmented) {
       const uint64_t n_ovf = *reinterpret_cast<uint64_t*>(ws->h_scalars), stored = *reinterpret_cast<uint64_t*>(ws->h_scalars + 8);
       *n = stored + n_ovf;
@@ -347,12 +399,12 @@ int lower_utf8_host(const LowerTable& lt, const uint8_t* in, int64_t len, std::v
 
 // Host model of filter_kernel's two filter levels (am_filter.cu: fk_probe16 / fk_probe16_s2, fk_phase_a) on the host image,
 // with the very cell / hash functions the kernel uses (am_internal.h).  IgnoreCase: `d` is the ORIGINAL text; both levels
-// see it folded (fold8), as in the kernel.
+// see it folded (every byte | 0x20), as in the kernel.
 void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uint32_t align, uint8_t* out_flags) {
   const bool ic = H.case_sensitivity == AM_IGNORE_CASE;
   auto byte_at = [&](uint64_t i) -> uint32_t {   // the kernel sees arbitrary bytes beyond the text: any value may only ADD candidates
     const uint32_t b = i < n ? d[i] : 0u;
-    return ic ? (fold8(b) & 0xFFu) : b;
+    return ic ? (b | 0x20u) : b;
   };
   auto gram4 = [&](uint64_t i) -> uint32_t { return byte_at(i) | byte_at(i + 1) << 8 | byte_at(i + 2) << 16 | byte_at(i + 3) << 24; };
   const bool exact = H.t2_exact != 0;
@@ -362,13 +414,17 @@ void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uin
   const uint32_t qmask = qgram_mask(q);
   for (uint64_t i = 0; i < n; i++) {
     uint32_t level1;
-    if (filter_is_s2(q)) {
-      // stride-2 cells: an even virtual position p tests cell A of its own q-gram, the odd position p + 1 cell B; the row is
-      // hashed from the q - 1 bytes the two share (for the odd position i these are text[i .. i+q-1), for the even one text[i+1 .. i+q))
+    if (q > 4) {
+      // long q-gram: one cell per needle, two bits of its word, probed at every position
+      uint32_t row, by, bt;
+      long_cell((uint64_t)gram4(i) | ((uint64_t)gram4(i + 4) << 32), q, &row, &by, &bt);   // (long_cell reads bytes 0..3 and q-4..q-1)
+      level1 = (H.filter[row] >> by) & (H.filter[row] >> bt) & 1u;
+    } else if (filter_is_s2(q)) {
+      // stride-2 cells: an even virtual position p tests cell A of its own 4-gram, the odd position p + 1 cell B; the row is
+      // hashed from the 3 bytes the two share (for the odd position i these are text[i .. i+3), for the even one text[i+1 .. i+4))
       const bool odd = ((align + i) & 1) != 0;
-      const uint64_t b = odd ? i : i + 1;                                      // p + 1
-      const uint32_t row = s2_hash(q, gram4(b), q > 4 ? gram4(b + q - 4) : 0u) >> (32 - rowbits);
-      const uint32_t priv = odd ? byte_at(i + q - 1) : byte_at(i);             // text[p + q] resp. text[p]
+      const uint32_t row = ((odd ? gram4(i) : gram4(i + 1)) * HASH_MUL_S2) >> (32 - rowbits);
+      const uint32_t priv = odd ? byte_at(i + 3) : byte_at(i);                 // text[p + 4] resp. text[p]
       level1 = (H.filter[(size_t)row * copies] >> (31u - (priv & 31u))) & 1u;
     } else {
       uint32_t row, bit;
@@ -389,8 +445,8 @@ void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uin
       }
     } else if (q > 4) {
       const uint32_t hi = gram4(i + 4) & (q >= 8 ? 0xFFFFFFFFu : 0xFFFFu);
-      const uint32_t b0 = t2q_bit0(g, hi), b1 = t2q_bit1(g, hi);
-      level2 = (H.filter2[b0 >> 5] >> (b0 & 31)) & (H.filter2[T2Q_WORD1 + (b1 >> 5)] >> (b1 & 31)) & 1u;
+      const uint32_t b0 = gq_hash(g, hi) >> (32 - H.gbits_log2);
+      level2 = (H.gbits[b0 >> 5] >> (b0 & 31)) & 1u;
     } else if (q == 4) {
       const uint32_t nb = byte_at(i + 4);
       const uint32_t ba = t2a_bit(g), bb = t2b_bit(g, nb), bc = t2c_bit(g, nb);
@@ -443,8 +499,9 @@ static int build_image(const am_automaton* a, int cs, Image** out) {
   if (H.filter2.empty()) { H.filter2.assign(T2_WORDS, 0); }
   if (H.jump.empty()) { H.jump.assign(16, JumpSlot{0, NONE, 0, 0}); H.jump_mask = 15; }
   if (H.tails.empty()) H.tails.assign(4, 0);
+  if (H.gbits.empty()) H.gbits.assign(4, 0);
   if ((rc = upload(im, H.dense, &D.dense)) || (rc = upload(im, H.fail, &D.fail)) || (rc = upload(im, H.edges, &D.edges)) ||
-      (rc = upload(im, H.jump, &D.jump)) || (rc = upload(im, H.tails, &D.tails)) || (rc = upload(im, H.filter, &D.filter)) || (rc = upload(im, H.filter2, &D.filter2)) ||
+      (rc = upload(im, H.jump, &D.jump)) || (rc = upload(im, H.tails, &D.tails)) || (rc = upload(im, H.filter, &D.filter)) || (rc = upload(im, H.filter2, &D.filter2)) || (rc = upload(im, H.gbits, &D.gbits)) ||
       (rc = upload(im, H.own_off, &D.own_off)) || (rc = upload(im, H.own_rank, &D.own_rank)) ||
       (rc = upload(im, H.first_out, &D.first_out)) || (rc = upload(im, H.next_out, &D.next_out)) ||
       (rc = upload(im, H.chain_count, &D.chain_count)) || (rc = upload(im, H.id_of_rank, &D.id_of_rank)) ||
@@ -458,7 +515,7 @@ static int build_image(const am_automaton* a, int cs, Image** out) {
   D.q = H.q; D.qmask = qgram_mask(H.q); D.min_len = H.min_len; D.max_len = H.max_len; D.rank_bits = H.rank_bits;
   D.num_states = H.num_states; D.num_needles = H.num_needles;
   D.ignore_case = cs == AM_IGNORE_CASE; D.halo = (uint32_t)H.halo_bytes;
-  D.t2_exact = H.t2_exact; D.t2_empty_key = H.t2_empty_key;
+  D.t2_exact = H.t2_exact; D.t2_empty_key = H.t2_empty_key; D.gbits_shift = 32 - H.gbits_log2;
   D.cdfa_states = H.cdfa_states; D.cdfa_shift = H.cdfa_shift;
   *out = im;
   return AM_OK;
@@ -485,6 +542,7 @@ int get_image(const am_automaton* ca, int cs, Image** out) {
 
 // Every compute entry point starts with this: image of the case mode, on its device (restored when `g` dies).
 #define AM_ENTER(a, cs)                                   \
+  AM_NVTX(__func__);                                      \
   Image* im = nullptr;                                    \
   DeviceGuard guard;                                      \
   { int rc_ = get_image((a), (cs), &im); if (rc_) return rc_; rc_ = check_ready(im, &guard); if (rc_) return rc_; }
@@ -593,8 +651,7 @@ int am_count_matches_dev(const am_automaton* a, int cs, const am_dev_text* t, vo
   AM_ENTER(a, cs);
   Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(im, ws, *t, MODE_COUNT, st);
-  if (!rc) rc = read_scalars(ws, st);
+  rc = scan_sync(im, ws, *t, MODE_COUNT, st);
   if (!rc) *out_count = *reinterpret_cast<uint64_t*>(ws->h_scalars);
   release_ws(im, ws);
   return rc;
@@ -606,9 +663,16 @@ int am_contains_any_dev(const am_automaton* a, int cs, const am_dev_text* t, voi
   AM_ENTER(a, cs);
   Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(im, ws, *t, MODE_ANY, st);
-  if (!rc) rc = read_scalars(ws, st);
-  if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
+  // window by window (1 GiB of end positions each, with the halo before it): the fold's `Done` -- the scan stops at the first
+  // window that holds a match
+  *out_bool = 0;
+  const uint64_t W = 1ull << 30, halo = im->host.halo_bytes;
+  for (uint64_t b = std::min(t->report_begin, t->text_len); !rc && b < t->text_len && !*out_bool; b += W) {
+    const uint64_t e = std::min(t->text_len, b + W), w = b > halo ? b - halo : 0;
+    am_dev_text win{static_cast<const uint8_t*>(t->dev_text) + w, e - w, b - w, t->pos_base + w};
+    rc = scan_sync(im, ws, win, MODE_ANY, st);
+    if (!rc) *out_bool = *reinterpret_cast<int*>(ws->h_scalars + 8) != 0;
+  }
   release_ws(im, ws);
   return rc;
 }
@@ -646,6 +710,19 @@ int am_find_all_dev(const am_automaton* a, int cs, const am_dev_text* t, void* s
 }
 
 // ---- multi-GPU: scan + all-gather of the counts, one host round trip (am_comm.cu holds the communicator) ---------------
+// The value a rank gathers carries bit 63 when its filter scan listed more survivors than its list holds (its counters
+// are then incomplete).  Every rank sees every value, so all of them take the same decision: repeat the round (the rank
+// concerned has grown its list) until no flag is raised -- no rank is ever alone in a collective.
+constexpr uint64_t SHARD_RETRY = 1ull << 63;
+static bool shard_round_done(const am_comm* c, Workspace* ws, int* rc) {
+  const uint64_t* g = reinterpret_cast<const uint64_t*>(ws->h_scalars + 64);
+  bool retry = false;
+  for (int i = 0; i < comm_size(c); i++) retry = retry || (g[i] & SHARD_RETRY) != 0;
+  bool again = false;
+  *rc = scan_overflowed(ws, &again);               // grows this rank's list when it was the one
+  return !retry || *rc != AM_OK;
+}
+
 int am_count_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_text* shard, void* stream, am_shard_result* out) {
   int rc = check_dev_text(shard); if (rc) return rc;
   if (!out || !c) return fail(AM_E_BADARG, "null argument");
@@ -653,9 +730,15 @@ int am_count_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_tex
   if ((rc = comm_check(c, im->device))) return rc;
   Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(im, ws, *shard, MODE_COUNT, st);
-  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars, ws->d_scalars + 64, st);            // this rank's count -> every rank's
-  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+  unsigned long long* ds = reinterpret_cast<unsigned long long*>(ws->d_scalars);
+  for (int round = 0; !rc; round++) {
+    rc = launch_scan(im, ws, *shard, MODE_COUNT, st);
+    if (!rc && launch_shard_total(ds, 0, 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);       // this rank's count -> every rank's
+    if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
+  }
   if (!rc) comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), out);
   release_ws(im, ws);
   return rc;
@@ -668,9 +751,15 @@ int am_contains_any_sharded(const am_automaton* a, int cs, am_comm* c, const am_
   if ((rc = comm_check(c, im->device))) return rc;
   Workspace* ws = acquire_ws(im); if (!ws) return fail(AM_E_OOM, "workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = launch_scan(im, ws, *shard, MODE_ANY, st);                                          // d_scalars[8..16): this shard's flag (0 / 1)
-  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 8, ws->d_scalars + 64, st);
-  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+  unsigned long long* ds = reinterpret_cast<unsigned long long*>(ws->d_scalars);
+  for (int round = 0; !rc; round++) {
+    rc = launch_scan(im, ws, *shard, MODE_ANY, st);                                        // d_scalars[8..16): this shard's flag (0 / 1)
+    if (!rc && launch_shard_total(ds, 1, 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
+    if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
+  }
   if (!rc) {
     am_shard_result r;
     comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), &r);
@@ -689,20 +778,21 @@ int am_find_all_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint64_t span = shard->text_len - std::min(shard->report_begin, shard->text_len);
   rc = ws->need_keys(std::max<uint64_t>(1u << 16, span / 512));
-  // scan, segment scan and segment sort are queued; the match count is d_scalars[0..8) + d_scalars[8..16) whatever path the
-  // ordering takes afterwards, so the all-gather goes on the stream right behind them and the host waits ONCE
-  if (!rc) rc = emit_enqueue(im, ws, *shard, st, dev_out, dev_out ? cap : 0);
-  if (!rc) {
-    cudaError_t e = launch_sum2(reinterpret_cast<const unsigned long long*>(ws->d_scalars), ws->emit_segmented ? 2 : 1,
-                                reinterpret_cast<unsigned long long*>(ws->d_scalars + 32), st);
-    if (e != cudaSuccess) rc = cuda_fail(e, "count kernel");
+  unsigned long long* ds = reinterpret_cast<unsigned long long*>(ws->d_scalars);
+  // scan, verification, segment scan and segment sort are queued; the match count is d_scalars[0..8) + d_scalars[8..16) whatever
+  // path the ordering takes afterwards, so the all-gather goes on the stream right behind them and the host waits ONCE
+  for (int round = 0; !rc; round++) {
+    rc = emit_enqueue(im, ws, *shard, st, dev_out, dev_out ? cap : 0);
+    if (!rc && launch_shard_total(ds, 0, ws->emit_segmented ? 2 : 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
+    if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
+    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
   }
-  if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
-  if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
   if (!rc) {
     comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), out);
     uint64_t n = 0;
-    rc = finish_find_all_dev(im, ws, *shard, st, dev_out, cap, &n);                        // (a rescan never changes the count)
+    rc = finish_find_all_dev(im, ws, *shard, st, dev_out, cap, &n);                        // (a rescan for more key space never changes the count)
     if (n != out->n_local && (rc == AM_OK || rc == AM_E_OVERFLOW)) rc = fail(AM_E_INTERNAL, "sharded match count changed between scan and ordering");
   }
   release_ws(im, ws);
@@ -797,8 +887,7 @@ static int scan_host_pipelined(const Image* a, Workspace* ws, const am_u8slice& 
   if (out_count) *out_count = 0;
   if (out_any) *out_any = 0;
   return for_each_host_chunk(a, ws, hay, [&](const am_dev_text& t, cudaStream_t st) -> int {
-    int rc = launch_scan(a, ws, t, mode, st);
-    if (!rc) rc = read_scalars(ws, st);
+    int rc = scan_sync(a, ws, t, mode, st);
     if (rc) return rc;
     if (out_count) *out_count += *reinterpret_cast<uint64_t*>(ws->h_scalars);
     if (out_any && *reinterpret_cast<int*>(ws->h_scalars + 8) != 0) { *out_any = 1; return -1; }

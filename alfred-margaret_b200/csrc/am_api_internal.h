@@ -2,7 +2,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler (nsys, ncu --nvtx) injects itself
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,11 +29,14 @@ struct Workspace {
   uint32_t* seg_counts = nullptr; size_t seg_counts_bytes = 0;
   uint64_t* seg_bases = nullptr; size_t seg_bases_bytes = 0;
   uint32_t* seen_bits = nullptr; size_t seen_bytes = 0;        // containsAll: bit per needle rank
+  ulonglong2* surv = nullptr; size_t surv_bytes = 0;           // filter scan: the survivor list {text index, 8 text bytes} between filter_kernel and verify_kernel
   cudaStream_t copy_stream = nullptr, scan_stream = nullptr;   // host-buffer scans: upload chunk k + 1 while chunk k is scanned
   cudaEvent_t copy_done[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;                    // profiling: around the scan kernel(s) of the last launch_scan
   bool emit_segmented = false; uint64_t num_segs = 0; uint32_t seg_cap = 0; uint64_t ovf_base = 0, ovf_cap = 0;
   int last_kernel = 0;                                         // kernel the last launch_scan really ran: 1 = walk, 2 = filter
+  uint64_t last_span = 0;                                      // bytes the last launch_scan reported on
+  bool force_walk = false;                                     // the next launch_scan takes the walk kernel (hand-over after a survivor flood)
   ~Workspace();
   int need_keys(uint64_t n);
   int need_sort_temp(size_t bytes);
@@ -40,6 +45,7 @@ struct Workspace {
   int need_aux(uint64_t a_bytes, uint64_t b_bytes);
   int need_segs(uint64_t n);
   int need_seen(uint64_t bits);
+  int need_surv(uint64_t entries);
 };
 
 // One case mode of an automaton: the host image and its copy in HBM.  Immutable once built.
@@ -51,6 +57,12 @@ struct Image {
   std::vector<void*> dev_allocs;
   std::mutex ws_mutex;
   std::vector<Workspace*> ws_pool;
+  // Survivor-rate monitor of the filter scan: texts on which the filter passes more than 1 / 16 of the positions (needles
+  // made of the text's most frequent q-grams, "aaaa..." against "aaaa") are handed over to the per-segment walk, whose cost
+  // does not depend on the text -- the reference's loop is O(n) on any input (Automaton.hs:489-510).  After two
+  // hand-overs in a row the filter is only tried on every eighth scan.
+  std::atomic<int> walk_streak{0};
+  std::atomic<unsigned> scans{0};
   ~Image();
 };
 
@@ -67,6 +79,13 @@ struct DeviceGuard {
   ~DeviceGuard() { if (active && prev >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev); } }
 };
 
+// NVTX range around an ABI entry point (ranges at the C-ABI entry points), closed when the scope ends.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define AM_NVTX(name) ::am::NvtxRange nvtx_range_(name)
+
 extern thread_local std::string g_last_error;
 extern thread_local uint64_t g_last_passes, g_last_rescans;
 extern thread_local float g_last_replacer_ms;
@@ -82,7 +101,8 @@ int check_ready(const Image* a, DeviceGuard* g);
 Workspace* acquire_ws(const Image* a);
 void release_ws(const Image* a, Workspace* w);
 int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cudaStream_t st);
-int read_scalars(Workspace* ws, cudaStream_t st, size_t bytes = 16);
+int read_scalars(Workspace* ws, cudaStream_t st, size_t bytes = 64);
+int scan_overflowed(const Image* a, Workspace* ws, bool* again);
 int emit_enqueue(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, am_match* matches, uint64_t matches_cap);
 int emit_finish(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_t st, uint64_t* n, am_match* matches, uint64_t matches_cap, bool* unpacked);
 // `matches` (nullable, device): when the keys could be ordered by the per-segment sort, the am_match records are written

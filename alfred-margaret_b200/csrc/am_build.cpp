@@ -88,12 +88,15 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   // (same needle id).  A needle with a code point that is not its own lower case can never match (the reference
   // lowers every text code point, Automaton.hs:478-480) and is not inserted at all.
   std::unordered_map<uint32_t, std::vector<uint32_t>> preimages;   // lowered cp -> length-changing pre-images
+  std::unordered_map<uint32_t, std::vector<uint32_t>> same_pre;    // lowered cp -> pre-images of the same UTF-8 length (filter cells, step 8)
   std::unordered_set<uint32_t> image;
+  std::vector<std::vector<uint8_t>> inserted;                      // every byte string the trie holds (needles and their variants)
   A->ic_copy_exact = true;
   if (cs == AM_IGNORE_CASE && lower)
     for (size_t i = 0; i < lower->n; i++) {
       const uint32_t from = lower->pairs[i].from_cp, to = lower->pairs[i].to_cp;
       if (from >= 128 && utf8_len(from) != utf8_len(to)) preimages[to].push_back(from);
+      else if (from >= 128 && from != to) same_pre[to].push_back(from);
       image.insert(to);
     }
   // A code point can occur in the lowered stream iff it is its own lower case or the image of another one.
@@ -134,7 +137,7 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
     uint32_t s = 0;
     for (uint32_t k = 0; k < len; k++) s = B.add(s, d[k]);
     terms.emplace_back(s, id);
-    if (len > 0) { A->min_len = std::min(A->min_len, len); A->max_len = std::max(A->max_len, len); }
+    if (len > 0) { A->min_len = std::min(A->min_len, len); A->max_len = std::max(A->max_len, len); inserted.emplace_back(d, d + len); }
   };
   for (size_t i = 0; i < n; i++) {
     if (needles[i].len < 0 || needles[i].off < 0 || (needles[i].len > 0 && !needles[i].ptr)) { *err = "bad needle slice"; return AM_E_BADARG; }
@@ -352,54 +355,108 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
   // q = the shortest needle's length up to 4; needle sets too large for the exact second level whose shortest needle
   // has >= 6 (>= 8) bytes take 6- (8-)grams: the bitmaps then answer for more of every needle, and a set of 10^5
   // needles over a small alphabet -- every 4-gram of which is some needle's prefix -- still filters.
-  A->q = 0; A->filter_keys = 0;
+  //
+  // The two filter levels are built from "gram instances": (first q bytes, byte q or CLOSED) of every string the trie
+  // holds.  IgnoreCase: of every CASE VARIANT of those strings' first code points -- each code point replaced by any of its
+  // same-length pre-images under the caller's toLower table (é <- É, я <- Я, ǳ <- ǲ Ǳ) -- folded (| 0x20: ASCII letters).
+  // So the kernel can probe the ORIGINAL text folded with one OR per word and never lowers a code point in its hot loop.
+  A->q = 0; A->filter_keys = 0; A->ic_fold_ok = true;
   if (A->num_empty == 0 && A->min_len > 0) {
     const bool ic = cs == AM_IGNORE_CASE;
-    auto keys_at_depth = [&](uint32_t q, std::vector<std::pair<uint64_t, uint32_t>>* keys) {   // (q-gram, state at depth q)
-      keys->clear();
-      for (uint32_t s = 0; s < S; s++) {
-        if (A->depth[s] != q) { if (A->depth[s] > q) break; continue; }
-        uint64_t g = 0; uint32_t t = s;
-        for (uint32_t k = q; k-- > 0;) { g |= (uint64_t)A->in_byte[t] << (8 * k); t = A->parent[t]; }
-        keys->emplace_back(g, s);
+    constexpr uint32_t CLOSED = 0x100u;
+    constexpr size_t MAX_CASE_VARIANTS = 256;
+    struct Instance { uint64_t gram; uint32_t next; };
+    auto gram_mask = [](uint32_t q) -> uint64_t { return q >= 8 ? ~0ull : ((1ull << (8 * q)) - 1ull); };
+    auto instances_of = [&](uint32_t q, std::vector<Instance>* out) {
+      std::unordered_map<uint64_t, std::vector<uint16_t>> seen;   // gram -> `next` values already emitted
+      out->clear();
+      auto emit = [&](const uint8_t* b, size_t len) {
+        uint64_t g = 0;
+        for (uint32_t k = 0; k < q; k++) g |= (uint64_t)b[k] << (8 * k);
+        uint32_t nx = len > q ? b[q] : CLOSED;
+        if (ic) { g = (g | 0x2020202020202020ull) & gram_mask(q); if (nx != CLOSED) nx |= 0x20u; }
+        auto& v = seen[g];
+        if (std::find(v.begin(), v.end(), (uint16_t)nx) == v.end()) { v.push_back((uint16_t)nx); out->push_back(Instance{g, nx}); }
+      };
+      std::vector<uint8_t> buf;
+      for (const auto& str : inserted) {
+        if (str.size() < q) continue;                          // (cannot happen: q <= min_len)
+        if (!ic) { emit(str.data(), str.size()); continue; }
+        // code points that reach into bytes [0, q]: their case variants
+        std::vector<std::vector<uint32_t>> opts;
+        std::vector<uint32_t> cps;
+        uint32_t covered = 0;
+        size_t combos = 1;
+        while (covered < std::min<size_t>(str.size(), q + 1)) {
+          uint32_t c; covered += decode(str.data(), (uint32_t)str.size(), covered, &c);
+          cps.push_back(c);
+          std::vector<uint32_t> o{c};
+          auto it = same_pre.find(c);
+          if (c >= 128 && it != same_pre.end()) for (uint32_t f : it->second) if (utf8_len(f) == utf8_len(c)) o.push_back(f);
+          combos *= o.size();
+          opts.push_back(std::move(o));
+        }
+        if (combos > MAX_CASE_VARIANTS) { A->ic_fold_ok = false; combos = 1; for (auto& o : opts) o.resize(1); }   // this automaton scans a lowered copy instead
+        std::vector<size_t> choice(opts.size(), 0);
+        for (size_t v = 0; v < combos; v++) {
+          buf.clear();
+          for (size_t p = 0; p < opts.size(); p++) encode(opts[p][choice[p]], &buf);
+          buf.insert(buf.end(), str.begin() + std::min<size_t>(covered, str.size()), str.end());   // (only the length matters beyond byte q)
+          emit(buf.data(), buf.size());
+          for (size_t p = 0; p < opts.size(); p++) { if (++choice[p] < opts[p].size()) break; choice[p] = 0; }
+        }
       }
     };
-    auto folded = [&](uint64_t g, uint32_t q) -> uint64_t { return ic ? (fold8_64(g) & (q >= 8 ? ~0ull : ((1ull << (8 * q)) - 1ull))) : g; };
-    std::vector<std::pair<uint64_t, uint32_t>> keys;
+    auto distinct_grams = [](const std::vector<Instance>& v) { std::unordered_set<uint64_t> d; for (auto& x : v) d.insert(x.gram); return d.size(); };
+    std::vector<Instance> inst;
     A->q = std::min<uint32_t>(4, A->min_len);
-    keys_at_depth(A->q, &keys);
-    {  // the exact second level holds the distinct (folded) q-grams: does it fit?
-      std::unordered_set<uint64_t> distinct;
-      for (auto& kv : keys) distinct.insert(folded(kv.first, A->q));
-      A->t2_exact = distinct.size() <= T2_MAX_EXACT_KEYS;
-    }
-    if (!A->t2_exact && FK_S2 && A->min_len >= 6) {
+    instances_of(A->q, &inst);
+    A->t2_exact = distinct_grams(inst) <= T2_MAX_EXACT_KEYS;  // the exact second level holds the distinct (folded) q-grams: does it fit?
+    if (!A->t2_exact && A->min_len >= 6) {
       A->q = A->min_len >= 8 ? 8 : 6;
-      keys_at_depth(A->q, &keys);
+      instances_of(A->q, &inst);
     }
     const uint32_t q = A->q;
-    A->filter_keys = (uint32_t)keys.size();
+    // ---- level 1: bitmap cells of every distinct (folded) gram --------------------------------------------------------
     A->filter.assign(FILTER_WORDS, 0);
+    const int copies = filter_copies(q, A->t2_exact != 0);
+    {
+      std::unordered_set<uint64_t> done;
+      for (auto& x : inst) {
+        if (!done.insert(x.gram).second) continue;
+        if (q > 4) {             // long q-gram: one cell, two bits of its word (stride-1 probe)
+          uint32_t row, by, bt;
+          long_cell(x.gram, q, &row, &by, &bt);
+          A->filter[row] |= (1u << by) | (1u << bt);
+        } else if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
+          uint32_t ra, ba, rb, bb;
+          filter_cells_s2((uint32_t)x.gram, filter_rowbits(copies), &ra, &ba, &rb, &bb);
+          for (int c = 0; c < copies; c++) {
+            A->filter[(size_t)ra * copies + c] |= 1u << ba;
+            A->filter[(size_t)rb * copies + c] |= 1u << bb;
+          }
+        } else {
+          uint32_t row, bit;
+          filter_cell((uint32_t)x.gram, &row, &bit);
+          for (int c = 0; c < copies; c++) A->filter[(size_t)row * copies + c] |= 1u << bit;
+        }
+      }
+    }
+    // ---- jump table: exact q-gram -> trie state (or the tail of its single needle path) -----------------------------------
+    std::vector<std::pair<uint64_t, uint32_t>> keys;          // (q-gram, state at depth q)
+    for (uint32_t s = 0; s < S; s++) {
+      if (A->depth[s] != q) { if (A->depth[s] > q) break; continue; }
+      uint64_t g = 0; uint32_t t = s;
+      for (uint32_t k = q; k-- > 0;) { g |= (uint64_t)A->in_byte[t] << (8 * k); t = A->parent[t]; }
+      keys.emplace_back(g, s);
+    }
+    A->filter_keys = (uint32_t)keys.size();
     uint32_t cap = next_pow2((uint64_t)keys.size() * 2 + 16);
     A->jump.assign(cap, JumpSlot{0, NONE, 0, 0});
     A->tails.clear();
     A->jump_mask = cap - 1;
     const uint32_t tail_from = std::min<uint32_t>(q, 4);       // the tail of a slot starts at this needle byte
-    const int copies = filter_copies(q, A->t2_exact != 0);
     for (auto& kv : keys) {
-      const uint64_t gf = folded(kv.first, q);                 // IgnoreCase: cells of the folded q-gram
-      if (filter_is_s2(q)) {   // stride-2 probe: one cell per parity of the start position
-        uint32_t ra, ba, rb, bb;
-        filter_cells_s2(gf, q, filter_rowbits(copies), &ra, &ba, &rb, &bb);
-        for (int c = 0; c < copies; c++) {
-          A->filter[(size_t)ra * copies + c] |= 1u << ba;
-          A->filter[(size_t)rb * copies + c] |= 1u << bb;
-        }
-      } else {
-        uint32_t row, bit;
-        filter_cell((uint32_t)gf, &row, &bit);
-        for (int c = 0; c < copies; c++) A->filter[(size_t)row * copies + c] |= 1u << bit;
-      }
       const uint32_t key_lo = (uint32_t)kv.first, key_hi = (uint32_t)(kv.first >> 32);
       uint32_t i = jump_hash(key_lo, key_hi) & A->jump_mask;
       while (A->jump[i].state != NONE) i = (i + 1) & A->jump_mask;
@@ -429,21 +486,17 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
       }
       A->jump[i] = slot;
     }
-    // second-level table (shared memory, 32 KiB): exact (folded) keys when they fit, else bitmaps
+    // ---- level 2 -----------------------------------------------------------------------------------------------------------
+    A->gbits.clear(); A->gbits_log2 = 0;
     if (A->t2_exact) {
-      // key -> aux: the (folded) byte that must follow the q-gram when every needle through it continues with that byte
+      // shared memory, 32 KiB: the exact (folded) keys; aux = the (folded) byte that must follow the q-gram when every
+      // string through it continues with that byte
       std::unordered_map<uint32_t, uint32_t> aux_of;
-      for (auto& kv : keys) {
-        const uint32_t g = (uint32_t)folded(kv.first, q), s = kv.second;
-        uint32_t aux = T2_AUX_ANY;
-        const bool has_own = A->own_off[s + 1] > A->own_off[s];
-        if (!has_own && A->child_off[s + 1] - A->child_off[s] == 1) {
-          aux = A->child_byte[A->child_off[s]];
-          if (ic) aux = fold8(aux) & 0xFFu;
-        }
+      for (auto& x : inst) {
+        const uint32_t g = (uint32_t)x.gram, aux = x.next == CLOSED ? T2_AUX_ANY : x.next;
         auto it = aux_of.find(g);
         if (it == aux_of.end()) aux_of.emplace(g, aux);
-        else if (it->second != aux) it->second = T2_AUX_ANY;   // several exact q-grams fold to this key and disagree
+        else if (it->second != aux) it->second = T2_AUX_ANY;
       }
       uint32_t empty = 0xFFFFFFFFu;  // any value that is not a key (a text q-gram equal to it is rejected later)
       while (aux_of.count(empty)) empty--;
@@ -465,24 +518,26 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
           hb = (hb + 1) & ((1u << T2_LOG2_BUCKETS) - 1);
         }
       }
+    } else if (q > 4) {
+      // global memory: a bitmap over the whole q-gram, ~256 bits per key, 2^20 .. 2^27 bits (128 KiB .. 16 MiB: L2-resident)
+      A->filter2.assign(T2_WORDS, 0);
+      const size_t nkeys = distinct_grams(inst);
+      A->gbits_log2 = 20;
+      while (A->gbits_log2 < 27 && (1ull << A->gbits_log2) < (uint64_t)nkeys * 256) A->gbits_log2++;
+      A->gbits.assign((size_t)1 << (A->gbits_log2 - 5), 0);
+      for (auto& x : inst) {
+        const uint32_t b = gq_hash((uint32_t)x.gram, (uint32_t)(x.gram >> 32)) >> (32 - A->gbits_log2);
+        A->gbits[b >> 5] |= 1u << (b & 31);
+      }
     } else {
       A->filter2.assign(T2_WORDS, 0);
       auto set_bit = [&](uint32_t word0, uint32_t bit) { A->filter2[word0 + (bit >> 5)] |= 1u << (bit & 31); };
-      for (auto& kv : keys) {
-        const uint64_t gf = folded(kv.first, q);
-        if (q < 4) { set_bit(0, filter2_bit((uint32_t)gf)); continue; }
-        if (q > 4) {                                           // Bloom filter over the whole q-gram, one bit per half
-          set_bit(0, t2q_bit0((uint32_t)gf, (uint32_t)(gf >> 32)));
-          set_bit(T2Q_WORD1, t2q_bit1((uint32_t)gf, (uint32_t)(gf >> 32)));
-          continue;
-        }
-        const uint32_t g = (uint32_t)gf, s = kv.second;       // q = 4: closed 4-grams + the 5-grams of the needles that go on
-        if (A->own_off[s + 1] > A->own_off[s]) set_bit(T2A_WORD0, t2a_bit(g));
-        for (uint32_t c = A->child_off[s]; c < A->child_off[s + 1]; c++) {
-          const uint32_t nb = ic ? (fold8(A->child_byte[c]) & 0xFFu) : A->child_byte[c];
-          set_bit(T2B_WORD0, t2b_bit(g, nb));
-          set_bit(T2C_WORD0, t2c_bit(g, nb));
-        }
+      for (auto& x : inst) {
+        const uint32_t g = (uint32_t)x.gram;
+        if (q < 4) { set_bit(0, filter2_bit(g)); continue; }
+        if (x.next == CLOSED) { set_bit(T2A_WORD0, t2a_bit(g)); continue; }   // q = 4: closed 4-grams + the 5-grams of the strings that go on
+        set_bit(T2B_WORD0, t2b_bit(g, x.next));
+        set_bit(T2C_WORD0, t2c_bit(g, x.next));
       }
     }
   }

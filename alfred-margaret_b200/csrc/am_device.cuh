@@ -19,7 +19,8 @@ struct DevAutomaton {
   const JumpSlot* jump;         // q-gram -> depth-q state (+ the tail of a simple sub-trie)
   const uint8_t* tails;         // tail bytes of the simple jump slots
   const uint32_t* filter;       // FILTER_WORDS words, bank-replicated q-gram bitmap
-  const uint32_t* filter2;      // second-level q-gram bitmap
+  const uint32_t* filter2;      // second-level table (shared-memory form)
+  const uint32_t* gbits;        // second-level bitmap of large needle sets (global memory, q > 4)
   const uint32_t* own_off;      // CSR of needles ending exactly at a state
   const uint32_t* own_rank;
   const uint32_t* first_out;    // output chain heads / links (walk kernel)
@@ -34,7 +35,7 @@ struct DevAutomaton {
   uint32_t dense_states, edge_mask, jump_mask;
   uint32_t q, qmask, min_len, max_len, rank_bits, num_states, num_needles;
   uint32_t ignore_case, halo;
-  uint32_t t2_exact, t2_empty_key;
+  uint32_t t2_exact, t2_empty_key, gbits_shift;
   uint32_t cdfa_states, cdfa_shift;
 };
 
@@ -52,6 +53,10 @@ struct ScanArgs {
   // filter kernel, IgnoreCase: 1 = `text` is the ORIGINAL text (one pass: folded probe, survivors lowered on the fly);
   // 0 = `text` is a lowered copy
   uint32_t ic_one_pass;
+  // filter scan: the positions that pass both filter levels (text indices) are listed here and verified by verify_kernel;
+  // *surv_count may exceed surv_cap (the list then holds the first surv_cap: the host repeats the scan with a larger list)
+  ulonglong2* surv; unsigned long long* surv_count; uint64_t surv_cap;   // entry: {text index, the eight text bytes at it}
+  uint32_t any_mode;            // containsAny: the kernels poll *d_flag and stop early
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)

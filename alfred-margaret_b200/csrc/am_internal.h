@@ -113,6 +113,8 @@ struct HostAutomaton {
   std::vector<uint8_t> tails;                   // tail bytes of the simple jump slots
   std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated
   std::vector<uint32_t> filter2;                // T2_WORDS: bitmap, or exact key buckets when t2_exact
+  std::vector<uint32_t> gbits; uint32_t gbits_log2 = 0;   // q > 4: second level in global memory (2^gbits_log2 bits)
+  bool ic_fold_ok = true;                       // IgnoreCase: the case variants of every needle's first code points fit the cells (one-pass scan)
   uint32_t t2_exact = 0, t2_empty_key = 0xFFFFFFFFu;
   uint32_t filter_keys = 0;                     // distinct q-grams
   LowerTable lower;
@@ -162,10 +164,10 @@ constexpr int filter_rowbits(int copies) { return copies == 32 ? 10 : copies == 
 constexpr int FILTER_ROWBITS_S1 = filter_rowbits(FK_COPIES_S1);
 static_assert((1 << filter_rowbits(FK_COPIES_S2)) * FK_COPIES_S2 == FILTER_WORDS && (1 << filter_rowbits(FK_COPIES_S2_BIG)) * FK_COPIES_S2_BIG == FILTER_WORDS &&
               (1 << FILTER_ROWBITS_S1) * FK_COPIES_S1 == FILTER_WORDS, "filter geometry");
-inline bool filter_is_s2(uint32_t q) { return FK_S2 && q >= 4; }
+inline bool filter_is_s2(uint32_t q) { return FK_S2 && q == 4; }
 // Copies of the bitmap for an automaton: `exact` = its q-grams fit the exact second-level table (t2_exact).
 constexpr int filter_copies_s2(bool exact) { return exact ? FK_COPIES_S2 : FK_COPIES_S2_BIG; }
-inline int filter_copies(uint32_t q, bool exact) { return filter_is_s2(q) ? filter_copies_s2(exact) : FK_COPIES_S1; }
+inline int filter_copies(uint32_t q, bool exact) { return q > 4 ? 1 : filter_is_s2(q) ? filter_copies_s2(exact) : FK_COPIES_S1; }
 // Filter cell of a (masked) q-gram: row and bit 0..31.  Must match the device code.
 inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
   const uint32_t x = g * HASH_MUL;
@@ -178,33 +180,40 @@ inline void filter_cell(uint32_t g, uint32_t* row, uint32_t* bit) {
 //   cell A (needle starts at the even position p):      row of (n1, n2, n3), bit chosen by n0
 //   cell B (needle starts at the odd position p + 1):   row of (n0, n1, n2), bit chosen by n3
 constexpr uint32_t HASH_MUL_S2 = HASH_MUL << 8;
-// Longer q-grams (needle sets whose shortest needle has >= 6 / >= 8 bytes and that are too large for the exact second
-// level): the row is hashed from the q - 1 bytes the two q-grams at p and p + 1 share, text[p+1 .. p+q), as
-//   y = X(p+1) * HASH_MUL + X(p+q-3) * (HASH_MUL_B << 8)
-// where X(i) is the 4-gram at i: the shifted multiplier drops the top byte of the second 4-gram, text[p+q], which is the
-// private byte of cell B.  X(p+q-3) is the first 4-gram of the next pair (q = 6) or of the pair after that (q = 8), so
-// the longer q-gram costs one more IMAD per pair.  Must match fk_probe16_s2.
-constexpr uint32_t HASH_MUL_B = 0xCC9E2D51u;
-constexpr uint32_t HASH_MUL_BS = HASH_MUL_B << 8;
-AM_HD_DECL uint32_t s2_hash(uint32_t q, uint32_t x1, uint32_t xk) { return q == 4 ? x1 * HASH_MUL_S2 : x1 * HASH_MUL + xk * HASH_MUL_BS; }
-// Stride-2 cells of a needle whose first q bytes are g (byte i at bits 8 i; q = 4, 6, 8):
-//   cell A (needle starts at the even position p):      row of bytes 1 .. q-1, bit chosen by byte 0
-//   cell B (needle starts at the odd position p + 1):   row of bytes 0 .. q-2, bit chosen by byte q-1
-inline void filter_cells_s2(uint64_t g, uint32_t q, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
-  const uint64_t sa = g >> 8;
-  *row_a = s2_hash(q, (uint32_t)sa, (uint32_t)(sa >> (8 * (q - 4)))) >> (32 - rowbits);
-  *bit_a = 31u - (uint32_t)(g & 31u);                        // the kernel rotates left by text[p] and tests bit 31
-  *row_b = s2_hash(q, (uint32_t)g, (uint32_t)(g >> (8 * (q - 4)))) >> (32 - rowbits);
-  *bit_b = 31u - (uint32_t)((g >> (8 * (q - 1))) & 31u);    // ... by text[p + q]
+// Stride-2 cells of a needle whose first 4 bytes are g (byte i at bits 8 i):
+//   cell A (needle starts at the even position p):      row of bytes 1 .. 3, bit chosen by byte 0
+//   cell B (needle starts at the odd position p + 1):   row of bytes 0 .. 2, bit chosen by byte 3
+inline void filter_cells_s2(uint32_t g, int rowbits, uint32_t* row_a, uint32_t* bit_a, uint32_t* row_b, uint32_t* bit_b) {
+  *row_a = ((g >> 8) * HASH_MUL_S2) >> (32 - rowbits);
+  *bit_a = 31u - (g & 31u);            // the kernel rotates left by text[p] and tests bit 31
+  *row_b = (g * HASH_MUL_S2) >> (32 - rowbits);
+  *bit_b = 31u - ((g >> 24) & 31u);    // ... by text[p + 4]
 }
-// IgnoreCase automata: the filter works on FOLDED bytes -- an ASCII byte | 0x20 (a letter and its upper case fold to the
-// same byte), a byte >= 0x80 | 0x3F (continuation bytes fold to 0xBF, lead bytes to 0xFF: `Char.toLower` may change any
-// byte of a multi-byte code point, but never which bytes are lead bytes as long as it keeps the UTF-8 length; code points
-// whose lower case has another length are kept and matched by needle variants).  Bitmap cells and the second level hold
-// folded q-grams and the kernel folds the text the same way before it probes, so the probe never sees `Char.toLower`:
+// Longer q-grams (q = 6, 8: needle sets too large for the exact second level whose shortest needle has >= 6 / >= 8 bytes).
+// A set of 10^5 needles would fill a sixth of the 1 Mi-bit bitmap with one-bit stride-2 cells (two per needle): a fifth of
+// all text positions would pass.  These sets take ONE cell per needle, probed at every position (stride 1), that sets TWO
+// bits of its word (a blocked Bloom filter, k = 2: ~3 % pass at 10^5 needles):
+//   t = X(p) * HASH_MUL                      X(i): the 4-gram at i
+//   y = t + X(p + q - 4) * HASH_MUL_B        all q bytes
+//   word = row (y >> 17);  bits 31 - (y & 31) and 31 - (t & 31): the kernel rotates the word left by y and by t
+// Must match fk_probe16_long.
+constexpr uint32_t HASH_MUL_B = 0xCC9E2D51u;
+constexpr int FILTER_ROWBITS_LONG = 15;       // one copy of the bitmap
+AM_HD_DECL void long_cell(uint64_t g, uint32_t q, uint32_t* row, uint32_t* bit_y, uint32_t* bit_t) {
+  const uint32_t t = (uint32_t)g * HASH_MUL;
+  const uint32_t y = t + (uint32_t)(g >> (8 * (q - 4))) * HASH_MUL_B;
+  *row = y >> (32 - FILTER_ROWBITS_LONG);
+  *bit_y = 31u - (y & 31u);
+  *bit_t = 31u - (t & 31u);
+}
+// IgnoreCase automata: the filter works on FOLDED bytes, every byte | 0x20 -- an ASCII letter and its upper case fold to
+// the same byte, every other byte only loses one bit.  `Char.toLower` above ASCII is not byte-local (Я D0 AF -> я D1 8F), so
+// the NEEDLE side enumerates instead: the bitmap cells and the second level hold the folded q-grams of every case variant
+// of a needle's first code points (the same-length pre-images of each code point under the caller's toLower table;
+// am_build.cpp step 8).  The kernel folds the text with one OR per word before it probes and never sees `Char.toLower`;
 // folding can add candidates, never lose one.  The survivors are verified on exactly lowered code points.
-AM_HD_DECL uint32_t fold8(uint32_t w) { return w | 0x20202020u | (((w >> 7) & 0x01010101u) * 0x3Fu); }
-AM_HD_DECL uint64_t fold8_64(uint64_t w) { return (uint64_t)fold8((uint32_t)w) | ((uint64_t)fold8((uint32_t)(w >> 32)) << 32); }
+constexpr uint32_t FOLD_MASK = 0x20202020u;
+AM_HD_DECL uint32_t fold20(uint32_t w) { return w | FOLD_MASK; }
 inline uint32_t filter2_bit(uint32_t g) { return (g * HASH_MUL2) >> (32 - FILTER2_LOG2_BITS); }
 // Second level for q = 4 needle sets too large for the exact table (T2_MAX_EXACT_KEYS): three bitmaps in the 32 KiB.
 //   T2A (64 Ki bits):  4-grams that END a needle (a needle of exactly four bytes);
@@ -215,13 +224,15 @@ constexpr int T2A_LOG2 = 16, T2B_LOG2 = 17, T2C_LOG2 = 16;
 constexpr uint32_t T2A_WORD0 = 0, T2B_WORD0 = (1u << T2A_LOG2) / 32, T2C_WORD0 = T2B_WORD0 + (1u << T2B_LOG2) / 32;
 static_assert(T2C_WORD0 + (1u << T2C_LOG2) / 32 == (uint32_t)T2_WORDS, "T2 bitmap geometry");
 constexpr uint32_t HASH_MUL3 = 0xC2B2AE35u;
-// Second level for q > 4: a partitioned Bloom filter over the whole q-gram (lo = bytes 0..3, hi = bytes 4..q-1), one bit in
-// each half of the 32 KiB (2 x 128 Ki bits).  Must match fk_phase_a.
-constexpr int T2Q_LOG2 = 17;
-constexpr uint32_t T2Q_WORD1 = (1u << T2Q_LOG2) / 32;
-static_assert(2 * T2Q_WORD1 == (uint32_t)T2_WORDS, "T2Q geometry");
-AM_HD_DECL uint32_t t2q_bit0(uint32_t lo, uint32_t hi) { return ((lo * HASH_MUL2) ^ (hi * HASH_MUL)) >> (32 - T2Q_LOG2); }
-AM_HD_DECL uint32_t t2q_bit1(uint32_t lo, uint32_t hi) { return ((lo ^ (hi * 0x01000193u) ^ (hi >> 15)) * HASH_MUL3) >> (32 - T2Q_LOG2); }
+// Second level for q > 4 (large needle sets): a bitmap over the whole q-gram (lo = bytes 0..3, hi = bytes 4..q-1) in
+// GLOBAL memory -- 2^20 .. 2^27 bits, ~256 bits per key, resident in the 126 MB L2 -- because 32 KiB of shared memory
+// cannot tell 10^5 keys apart.  The kernel looks the level-1 candidates up warp-cooperatively, 32 independent loads per
+// round (fk_global_rounds).  Must match the kernel.
+AM_HD_DECL uint32_t gq_hash(uint32_t lo, uint32_t hi) {
+  uint32_t h = (lo * HASH_MUL2) ^ (hi * HASH_MUL3);
+  h ^= h >> 15;
+  return h * HASH_MUL;
+}
 AM_HD_DECL uint32_t t2a_bit(uint32_t g4) { return (g4 * HASH_MUL2) >> (32 - T2A_LOG2); }
 AM_HD_DECL uint32_t t2b_bit(uint32_t g4, uint32_t b4) { return ((g4 * HASH_MUL2) ^ (b4 * HASH_MUL)) >> (32 - T2B_LOG2); }
 AM_HD_DECL uint32_t t2c_bit(uint32_t g4, uint32_t b4) { return ((g4 ^ (b4 * 0x01000193u)) * HASH_MUL3) >> (32 - T2C_LOG2); }

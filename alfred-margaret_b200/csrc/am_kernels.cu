@@ -527,14 +527,18 @@ cudaError_t launch_seg_compact(const uint64_t* seg_keys, const uint32_t* seg_cou
 // =====================================================================================================
 // small helpers of the sharded calls and of containsAll
 // =====================================================================================================
-__global__ void sum2_kernel(const unsigned long long* in, int n, unsigned long long* out) {
+// The value a rank contributes to the sharded calls' all-gather: the sum of `n` scan counters, with bit 63 raised when the
+// filter scan listed more survivors than its list holds (its counters are then incomplete and every rank repeats the round).
+__global__ void shard_total_kernel(const unsigned long long* in, int first, int n, const unsigned long long* surv_count, unsigned long long surv_cap, unsigned long long* out) {
   unsigned long long s = 0;
-  for (int i = 0; i < n; i++) s += in[i];
+  for (int i = 0; i < n; i++) s += in[first + i];
+  if (surv_cap && *surv_count > surv_cap) s |= 1ull << 63;
   *out = s;
 }
-cudaError_t launch_sum2(const unsigned long long* d_in, int n, unsigned long long* d_out, cudaStream_t st) {
+cudaError_t launch_shard_total(const unsigned long long* d_scalars, int first, int n, const unsigned long long* surv_count, unsigned long long surv_cap,
+                               unsigned long long* d_out, cudaStream_t st) {
   g_kernel_launches++;
-  sum2_kernel<<<1, 1, 0, st>>>(d_in, n, d_out);
+  shard_total_kernel<<<1, 1, 0, st>>>(d_scalars, first, n, surv_count, surv_cap, d_out);
   return cudaGetLastError();
 }
 

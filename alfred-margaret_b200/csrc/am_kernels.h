@@ -39,8 +39,9 @@ inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, std::atomic<uint64_t
 
 // Per-segment goto+failure walk (general path).  mode: ScanMode.
 cudaError_t launch_walk(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);
-// q-gram filter + goto verify (fast path; requires A.q > 0 and CaseSensitive).
+// q-gram filter scan (fast path; requires A.q > 0): filter_kernel lists the survivors, verify_kernel verifies them.
 cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_verify(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st);
 
 // IgnoreCase front end of the filter kernel: lowered copy of the text (+ count of length-changing code points).
 cudaError_t launch_lower(const DevAutomaton& A, const uint8_t* text, uint64_t text_len, uint8_t* out, unsigned int* exceptions, bool keep, cudaStream_t st);
@@ -59,8 +60,10 @@ size_t sort_temp_bytes(uint64_t n, int end_bit);
 cudaError_t sort_keys(void* temp, size_t temp_bytes, const uint64_t* in, uint64_t* out, uint64_t n, int end_bit, cudaStream_t st);
 cudaError_t launch_unpack(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, am_match* out, cudaStream_t st);
 int filter_kernel_smem_bytes();
-// out = in[0] + ... + in[n - 1] (one thread; joins the counters of a scan on the stream, ahead of the sharded calls' all-gather)
-cudaError_t launch_sum2(const unsigned long long* d_in, int n, unsigned long long* d_out, cudaStream_t st);
+// *d_out = d_scalars[first] + ... + d_scalars[first + n - 1], bit 63 raised when the survivor list overflowed (one thread; joins the
+// counters of a scan on the stream, ahead of the sharded calls' all-gather)
+cudaError_t launch_shard_total(const unsigned long long* d_scalars, int first, int n, const unsigned long long* surv_count, unsigned long long surv_cap,
+                               unsigned long long* d_out, cudaStream_t st);
 // containsAll: OR the needle ranks of keys[0..n) into the bit set `seen`, then *d_missing = needles not seen yet
 cudaError_t launch_mark_seen(const uint64_t* keys, uint64_t n, uint32_t rank_bits, uint32_t* seen, uint32_t num_needles, unsigned int* d_missing, cudaStream_t st);
 

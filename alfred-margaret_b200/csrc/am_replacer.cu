@@ -31,6 +31,8 @@ struct am_replacer {
   std::vector<uint32_t> len_bytes, len_cps, repl_off;   // Payload of needle i: lengths of the ORIGINAL needle (:111-113)
   std::vector<uint8_t> repl_bytes;
   uint8_t* d_repl = nullptr;
+  void* d_idinfo[2] = {nullptr, nullptr};  // per case mode: IdInfo of every needle id (rank in that image, replacement, payload lengths)
+  std::mutex mu;
   bool has_empty = false;
   bool stored_len_differs = false;       // some stored (lowered) needle has another byte length than the original
 };
@@ -267,9 +269,394 @@ __global__ void rescan_edits_kernel(DevAutomaton A, const uint8_t* text, uint64_
 
 }  // namespace
 
-// Replacer.runWithLimit (:203-242) on a device-resident text.  `d_in` is only read; the result is left in a buffer of the
-// library's: *d_out (cudaMalloc'ed, ownership passes to the caller), *out_len.
-static int replacer_core(const am_replacer* r, const Image* a, int cs, const uint8_t* d_in, uint64_t len, uint64_t max_len, cudaStream_t st,
+// =====================================================================================================================
+// Passes that cost O(edits), not O(text): the text lives in TILES
+// =====================================================================================================================
+// A pass of `runWithLimit` replaces the kept occurrences of ONE needle: a few thousand edits in a multi-GiB text.  Copying
+// the whole text per pass (`replace`, :163-180, is a Text.concat) made the passes of config C4 cost 2.9 ms each, all of it
+// the copy.  Here the text is cut into tiles of TILE_FILL bytes that sit in slots of TILE_CAP bytes, so a tile can grow or
+// shrink in place: a pass rewrites only the tiles its edits touch, the per-tile lengths are prefix-summed again
+// (tile_base), and every kernel that reads text does so through a TextView that maps a text position to (tile, offset).
+// The match list is carried from pass to pass in text coordinates as before: matches that touch no edit are shifted,
+// the neighbourhood of every edit is rescanned on the rewritten tiles.  A tile that would outgrow its slot sends that one
+// pass down the contiguous path (materialise, splice_kernel, re-tile).  All kernels of a pass are queued back to back
+// -- the needle of the pass, its match count and the number of kept edits stay on the device (PassScalars) -- and the host
+// waits ONCE per pass.
+constexpr uint32_t TILE_FILL = 4096, TILE_CAP = 8192;
+
+struct TextView {
+  const uint8_t* base;          // the contiguous text, or the tile slots (tile t at base + t * TILE_CAP)
+  uint64_t len;
+  const uint32_t* tile_len;     // tiled: bytes in tile t ...
+  const uint64_t* tile_base;    // ... and the text position of its first byte (num_tiles + 1 entries, the last one = len)
+  uint32_t num_tiles, tiled;
+};
+struct Cursor { uint64_t pos; uint32_t t, off; };
+
+__device__ __forceinline__ void cur_set(const TextView& v, Cursor& c, uint64_t pos) {   // pos < v.len
+  c.pos = pos;
+  if (v.tiled) {
+    uint32_t lo = 0, hi = v.num_tiles;                        // the last tile whose base is <= pos: it is not empty and holds pos
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(v.tile_base + mid) <= pos) lo = mid; else hi = mid; }
+    c.t = lo; c.off = (uint32_t)(pos - __ldg(v.tile_base + lo));
+  }
+}
+__device__ __forceinline__ uint32_t cur_byte(const TextView& v, const Cursor& c) {
+  return v.tiled ? __ldg(v.base + (size_t)c.t * TILE_CAP + c.off) : __ldg(v.base + c.pos);
+}
+__device__ __forceinline__ void cur_next(const TextView& v, Cursor& c) {                 // may step to v.len (then the cursor must not be read)
+  c.pos++;
+  if (v.tiled) {
+    c.off++;
+    while (c.off >= __ldg(v.tile_len + c.t) && c.t + 1 < v.num_tiles) { c.t++; c.off = 0; }
+  }
+}
+__device__ __forceinline__ void cur_prev(const TextView& v, Cursor& c) {                 // pos > 0
+  c.pos--;
+  if (v.tiled) {
+    if (c.off > 0) c.off--;
+    else { do { c.t--; } while (__ldg(v.tile_len + c.t) == 0); c.off = __ldg(v.tile_len + c.t) - 1; }
+  }
+}
+// skipCodePointsBackwards (Utf8.hs:256-276) from byte `pos` (inside a code point) back by n more code points; -1 where the
+// reference calls `error`.
+__device__ __forceinline__ long long skip_back(const TextView& v, uint64_t pos, long long n) {
+  Cursor c; cur_set(v, c, pos);
+  for (;;) {
+    if ((cur_byte(v, c) & 0xC0u) == 0x80u) { if (c.pos == 0) return -1; cur_prev(v, c); continue; }
+    if (n == 0) return (long long)c.pos;
+    if (c.pos == 0) return -1;
+    cur_prev(v, c); n--;
+  }
+}
+
+struct IdInfo { uint32_t rank, repl_off, repl_len, len_bytes, len_cps; };
+struct PassScalars {
+  unsigned int best;            // needle id of this pass (NONE: no match below the threshold)
+  int error;                    // skipCodePointsBackwards ran off the text
+  unsigned int overflow;        // some tile would outgrow its slot: nothing was rewritten
+  unsigned int ntouched;
+  long long delta_sum;          // replacementLength - text length over ALL matches of the needle, before removeOverlap (:240)
+  unsigned long long nsel;      // matches of the needle
+  unsigned long long nkept;     // after removeOverlap
+  long long total_shift;        // sum of the kept deltas
+  unsigned long long n_new;     // matches found around the edits of the rewritten text
+  unsigned long long n_carried; // matches carried over
+  IdInfo id;                    // of `best`
+};
+
+__global__ void pass_begin_kernel(PassScalars* sc) { PassScalars z; memset(&z, 0, sizeof z); z.best = NONE; *sc = z; }
+__global__ void pass_resolve_kernel(PassScalars* sc, const IdInfo* info) { if (sc->best != NONE) sc->id = info[sc->best]; }
+
+struct RankIsDev {
+  uint64_t mask; const PassScalars* sc;
+  __device__ bool operator()(const uint64_t& k) const { return sc->best != NONE && (uint32_t)(k & mask) == sc->id.rank; }
+};
+
+// start / length of every match of the pass's needle + sum of the length deltas (replacementLength); `n` lives on the device
+__global__ void starts_view_kernel(const uint64_t* sel, const PassScalars* sc, uint32_t rank_bits, TextView v, int ignore_case, uint64_t* start, uint64_t* end,
+                                   PassScalars* out) {
+  const uint64_t n = sc->nsel;
+  const uint32_t len_bytes = sc->id.len_bytes, len_cps = sc->id.len_cps;
+  const long long repl_len = sc->id.repl_len;
+  long long local = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t pos = sel[i] >> rank_bits;
+    uint64_t s;
+    if (!ignore_case) {
+      if (pos < len_bytes) { out->error = 1; s = 0; }
+      else s = pos - len_bytes;                              // makeMatch CaseSensitive (:268-269)
+    } else {
+      const long long idx = skip_back(v, pos - 1, (long long)len_cps - 1);   // makeMatch IgnoreCase (:271-274)
+      if (idx < 0) { out->error = 1; s = 0; } else s = (uint64_t)idx;
+    }
+    start[i] = s; end[i] = pos;
+    local += repl_len - (long long)(pos - s);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd((unsigned long long*)&out->delta_sum, (unsigned long long)local);
+}
+
+// removeOverlap (:191-198) with the count on the device.  Cluster heads are always kept; one WARP walks a cluster: its
+// lanes look 32 matches ahead at a time (a periodic text makes the whole list one cluster).
+__global__ void overlap_dev_kernel(const uint64_t* start, const uint64_t* end, const PassScalars* sc, uint8_t* keep) {
+  const uint64_t n = sc->nsel;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  // every warp takes the cluster heads among "its" 32-match slices
+  for (uint64_t base = warp * 32; base < n; base += nwarps * 32) {
+    const uint64_t j = base + lane;
+    const bool head = j < n && (j == 0 || start[j] >= end[j - 1]);
+    unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+    while (heads) {
+      const int hl = __ffs(heads) - 1;
+      heads &= heads - 1;
+      uint64_t k = base + hl;                                 // walk this cluster with the whole warp
+      if (lane == 0) keep[k] = 1;
+      uint64_t last_end = end[k];
+      k++;
+      for (;;) {
+        // the next kept match: the first k' >= k with start >= last_end, unless the cluster ends before it
+        const uint64_t kk = k + lane;
+        const bool in = kk < n;
+        const uint64_t s = in ? start[kk] : 0, e_prev = in ? end[kk - 1] : 0;
+        const unsigned brk = __ballot_sync(0xFFFFFFFFu, !in || s >= e_prev);     // cluster boundary (or the end of the list) at kk
+        const unsigned ok = __ballot_sync(0xFFFFFFFFu, in && s >= last_end);
+        const int b = brk ? __ffs(brk) - 1 : 32, o = ok ? __ffs(ok) - 1 : 32;
+        if (o < b) {                                          // a kept match inside the cluster
+          if (lane == 0) keep[k + o] = 1;
+          last_end = end[k + o];
+          k += o + 1;
+        } else if (b < 32) break;                             // the cluster ends first
+        else k += 32;                                         // neither in these 32: look further
+      }
+    }
+  }
+}
+
+__global__ void gather_kept_dev_kernel(const uint64_t* start, const uint64_t* end, const uint8_t* keep, const uint64_t* kept_index, uint64_t n_bound,
+                                       PassScalars* sc, uint64_t* k_start, uint64_t* k_end, long long* k_delta) {
+  const uint64_t n = sc->nsel;
+  const long long repl_len = sc->id.repl_len;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+    if (!keep[j]) continue;
+    const uint64_t k = kept_index[j];
+    k_start[k] = start[j]; k_end[k] = end[j]; k_delta[k] = repl_len - (long long)(end[j] - start[j]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc->nkept = kept_index[n_bound];
+}
+__global__ void total_shift_kernel(const long long* k_shift, uint64_t n_bound, PassScalars* sc) { sc->total_shift = k_shift[n_bound]; }
+
+// (a) of the carried list, on the text BEFORE the pass's edits: the matches of still-eligible needles that touch no
+// replaced span, shifted; every other key becomes DROPPED and an order-preserving compaction (DeviceSelect) follows, so
+// the carried list stays sorted and no pass sorts it again.  IgnoreCase: the span of a match starts len_cps code points
+// before its end; it is found by walking back only when an edit lies close enough to matter.
+constexpr uint64_t DROPPED = ~0ull;
+struct NotDropped { __host__ __device__ bool operator()(const uint64_t& k) const { return k != DROPPED; } };
+__global__ void carry_view_kernel(const uint64_t* keys, uint64_t n, uint32_t rank_bits, const uint32_t* id_of_rank, const uint32_t* len_of_rank, const IdInfo* info,
+                                  int ignore_case, TextView v, const uint64_t* k_start, const uint64_t* k_end, const long long* k_shift, uint64_t n_bound,
+                                  PassScalars* sc, uint64_t* out) {
+  const uint64_t mask = (1ull << rank_bits) - 1;
+  const uint64_t K = sc->nkept;
+  const uint32_t pass_id = sc->best;
+  const long long total_shift = k_shift[n_bound];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    const uint32_t rank = (uint32_t)(key & mask);
+    const uint32_t id = __ldg(id_of_rank + rank);
+    uint64_t res = DROPPED;
+    if (id > pass_id) {                                        // (else: at or above the new threshold, `pMatch < threshold`, :253)
+      const uint64_t e = key >> rank_bits;
+      uint64_t s;
+      if (!ignore_case) s = e - __ldg(len_of_rank + rank);
+      else { const uint64_t span = 4ull * __ldg(&info[id].len_cps); s = e > span ? e - span : 0; }   // earliest possible start
+      uint64_t lo = 0, hi = K;                                // first edit that ends after the match starts
+      while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (k_end[mid] > s) hi = mid; else lo = mid + 1; }
+      bool touched = lo < K && k_start[lo] < e;
+      if (touched && ignore_case) {
+        const long long es = skip_back(v, e - 1, (long long)__ldg(&info[id].len_cps) - 1);   // the exact start
+        if (es < 0) sc->error = 1;
+        else {
+          s = (uint64_t)es;
+          while (lo < K && k_end[lo] <= s) lo++;
+          touched = lo < K && k_start[lo] < e;
+        }
+      }
+      if (!touched) res = ((uint64_t)((long long)e + (lo < K ? k_shift[lo] : total_shift)) << rank_bits) | rank;
+    }
+    out[i] = res;
+  }
+}
+// Merge the (sorted) carried list A with the (sorted, small) list B of rescanned matches: the keys are distinct, so the
+// place of a key is its own index plus the number of keys of the other list below it.
+__global__ void merge_kernel(const uint64_t* A, uint64_t nA, const uint64_t* B, uint64_t nB, uint64_t* out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += (uint64_t)gridDim.x * blockDim.x) {
+    const bool fromA = i < nA;
+    const uint64_t key = fromA ? A[i] : B[i - nA];
+    const uint64_t* o = fromA ? B : A;
+    uint64_t lo = 0, hi = fromA ? nB : nA;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (o[mid] < key) lo = mid + 1; else hi = mid; }
+    out[(fromA ? i : i - nA) + lo] = key;
+  }
+}
+
+// ---- tiles -----------------------------------------------------------------------------------------------------------------
+__global__ void tileify_kernel(const uint8_t* src, uint64_t len, uint8_t* tiles, uint32_t* tile_len, uint32_t num_tiles) {
+  // 16-byte copies where the source allows it (tile t starts at src + t * 4096: as aligned as src itself)
+  const bool al = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint64_t b = (uint64_t)t * TILE_FILL;
+    const uint32_t n = (uint32_t)(len - b < TILE_FILL ? len - b : TILE_FILL);
+    uint8_t* d = tiles + (size_t)t * TILE_CAP;
+    if (al) {
+      const uint32_t nv = n >> 4;
+      for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(d)[i] = __ldg(reinterpret_cast<const uint4*>(src + b) + i);
+      for (uint32_t i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = src[b + i];
+    } else {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = src[b + i];
+    }
+    if (threadIdx.x == 0) tile_len[t] = n;
+  }
+}
+__global__ void materialize_kernel(const uint8_t* tiles, const uint32_t* tile_len, const uint64_t* tile_base, uint32_t num_tiles, uint8_t* dst) {
+  for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint32_t n = tile_len[t];
+    const uint8_t* s = tiles + (size_t)t * TILE_CAP;
+    uint8_t* d = dst + tile_base[t];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+  }
+}
+// The tiles an edit touches (the tile of its first byte .. the tile of its last byte), each listed once.
+__global__ void tile_mark_kernel(const PassScalars* sc, const uint64_t* k_start, const uint64_t* k_end, TextView v, uint32_t* tile_flag, uint32_t* touched, PassScalars* out) {
+  const uint64_t K = sc->nkept;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < K; j += (uint64_t)gridDim.x * blockDim.x) {
+    Cursor a, b;
+    cur_set(v, a, k_start[j]);
+    cur_set(v, b, k_end[j] - 1);                               // (spans are not empty: no empty needle in this form)
+    for (uint32_t t = a.t; t <= b.t; t++)
+      if (atomicExch(tile_flag + t, 1u) == 0u) touched[atomicAdd(&out->ntouched, 1u)] = t;
+  }
+}
+// New length of every touched tile; a tile that would outgrow its slot raises `overflow` and the pass rewrites nothing.
+// One thread per touched tile walks the (few) edits that intersect it.
+__device__ __forceinline__ uint64_t first_edit_after(const uint64_t* k_end, uint64_t K, uint64_t t0) {
+  uint64_t lo = 0, hi = K;
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (k_end[mid] > t0) hi = mid; else lo = mid + 1; }
+  return lo;
+}
+__global__ void tile_plan_kernel(PassScalars* sc, const uint32_t* touched, const uint64_t* k_start, const uint64_t* k_end, TextView v, uint32_t* new_len) {
+  const uint64_t K = sc->nkept;
+  const uint32_t rl = sc->id.repl_len, nt = sc->ntouched;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const uint32_t t = touched[i];
+    const uint64_t t0 = v.tile_base[t], t1 = t0 + v.tile_len[t];
+    long long len = (long long)v.tile_len[t];
+    for (uint64_t k = first_edit_after(k_end, K, t0); k < K && k_start[k] < t1; k++) {
+      const uint64_t a = k_start[k] > t0 ? k_start[k] : t0, b = k_end[k] < t1 ? k_end[k] : t1;
+      len -= (long long)(b - a);
+      if (k_start[k] >= t0) len += rl;                         // the tile that holds an edit's first byte writes its replacement
+    }
+    new_len[i] = (uint32_t)len;
+    if (len > (long long)TILE_CAP) sc->overflow = 1;
+  }
+}
+// Rewrite the touched tiles in place: the tile is staged in shared memory, the gaps between its edits are copied back
+// shifted, the replacements written in (`replace`, :163-180, one tile at a time).
+__global__ void __launch_bounds__(128) tile_splice_kernel(const PassScalars* sc, const uint32_t* touched, const uint32_t* new_len, const uint64_t* k_start, const uint64_t* k_end,
+                                                          uint8_t* tiles, uint32_t* tile_len, const uint64_t* tile_base, uint32_t* tile_flag, const uint8_t* repl_pool) {
+  __shared__ __align__(16) uint8_t in[TILE_CAP];
+  if (sc->overflow) {                                          // (the flags still have to be cleared for the next pass)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sc->ntouched; i += gridDim.x * blockDim.x) tile_flag[touched[i]] = 0;
+    return;
+  }
+  const uint64_t K = sc->nkept;
+  const uint32_t rl = sc->id.repl_len, nt = sc->ntouched;
+  const uint8_t* repl = repl_pool + sc->id.repl_off;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    const uint32_t t = touched[i];
+    const uint32_t n = tile_len[t];
+    const uint64_t t0 = tile_base[t], t1 = t0 + n;
+    uint8_t* tile = tiles + (size_t)t * TILE_CAP;
+    __syncthreads();
+    for (uint32_t x = threadIdx.x; x < (n + 15) / 16; x += blockDim.x) reinterpret_cast<uint4*>(in)[x] = reinterpret_cast<const uint4*>(tile)[x];
+    __syncthreads();
+    uint64_t k = first_edit_after(k_end, K, t0);
+    uint64_t cur = t0;                                         // next source byte to place
+    uint32_t out = 0;
+    if (k < K && k_start[k] < t0) { cur = k_end[k] < t1 ? k_end[k] : t1; k++; }   // an edit that began in an earlier tile swallows our first bytes
+    for (;;) {
+      const bool have = k < K && k_start[k] < t1;
+      const uint64_t gap_end = have ? k_start[k] : t1;
+      const uint32_t g = (uint32_t)(gap_end - cur), from = (uint32_t)(cur - t0);
+      for (uint32_t x = threadIdx.x; x < g; x += blockDim.x) tile[out + x] = in[from + x];
+      out += g;
+      if (!have) break;
+      for (uint32_t x = threadIdx.x; x < rl; x += blockDim.x) tile[out + x] = repl[x];
+      out += rl;
+      cur = k_end[k] < t1 ? k_end[k] : t1;
+      if (k_end[k] >= t1) break;                               // the rest of the tile is inside this edit
+      k++;
+    }
+    if (threadIdx.x == 0) { tile_len[t] = new_len[i]; tile_flag[t] = 0; }
+  }
+}
+
+// (b) of the carried list, on the REWRITTEN text: one thread per edit walks [new_start - halo, new_start + repl_len + halo) from
+// the root state and reports the matches that touch its edit; a match that touches several edits is reported by the last
+// one.  IgnoreCase walks lowered code points (decode, `Char.toLower` table, re-encode; a code point whose lower case has
+// another UTF-8 length is fed as it is: the automaton holds the variants) and finds a match's start by walking back.
+__global__ void rescan_view_kernel(DevAutomaton A, TextView v, const IdInfo* info, int ignore_case, const uint64_t* k_start, const long long* k_shift,
+                                   PassScalars* sc, uint64_t* out, uint64_t cap) {   // out: the pass's list of rescanned matches (unordered), counted in sc->n_new
+  if (sc->overflow || sc->best == NONE) return;
+  const uint64_t K = sc->nkept;
+  const uint32_t repl_len = sc->id.repl_len, pass_id = sc->best;
+  const uint64_t text_len = v.tiled ? v.tile_base[v.num_tiles] : v.len;   // (a pass is queued before the host knows the new length)
+  const uint64_t halo = A.halo;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < K; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t ns = (uint64_t)((long long)k_start[j] + k_shift[j]);          // the replacement occupies [ns, ns + repl_len)
+    const bool has_next = j + 1 < K;
+    const uint64_t ns2 = has_next ? (uint64_t)((long long)k_start[j + 1] + k_shift[j + 1]) : 0;
+    uint64_t p = ns > halo ? ns - halo : 0;
+    uint64_t end = ns + repl_len + halo; if (end > text_len) end = text_len;
+    if (p >= end) continue;
+    Cursor c; cur_set(v, c, p);
+    uint32_t state = 0, cp = 0, rem = 0, raw = 0, nraw = 0;
+    bool synced = !(ignore_case && p > 0);
+    for (; p < end; p++, cur_next(v, c)) {
+      const uint32_t byte = cur_byte(v, c);
+      uint32_t t;
+      if (!ignore_case) {
+        t = ac_step(A, state, byte);
+      } else {
+        if (!synced) { if ((byte & 0xC0u) == 0x80u) continue; synced = true; }   // start on a code point boundary
+        if (rem == 0 && byte < 0x80u) {
+          t = ac_step(A, state, byte + ((byte - 'A' < 26u) ? 0x20u : 0u));
+        } else {
+          if (rem == 0) { raw = 0; nraw = 0; cp = byte < 0xE0u ? byte & 0x1Fu : byte < 0xF0u ? byte & 0x0Fu : byte & 0x07u; rem = byte < 0xC0u ? 0u : byte < 0xE0u ? 1u : byte < 0xF0u ? 2u : 3u; if (byte < 0xC0u) cp = byte; }
+          else { cp = (cp << 6) | (byte & 0x3Fu); rem--; }
+          raw |= byte << (8 * nraw); nraw++;
+          if (rem != 0) continue;                              // the code point is not complete yet
+          uint32_t l = lower_cp(A, cp);
+          const uint32_t ln = l < 0x80u ? 1u : l < 0x800u ? 2u : l < 0x10000u ? 3u : 4u;
+          uint32_t enc = raw;
+          if (l != cp && ln == nraw) {
+            enc = ln == 1 ? l : ln == 2 ? (0xC0u | (l >> 6)) | ((0x80u | (l & 0x3Fu)) << 8)
+                : ln == 3 ? (0xE0u | (l >> 12)) | ((0x80u | ((l >> 6) & 0x3Fu)) << 8) | ((0x80u | (l & 0x3Fu)) << 16)
+                          : (0xF0u | (l >> 18)) | ((0x80u | ((l >> 12) & 0x3Fu)) << 8) | ((0x80u | ((l >> 6) & 0x3Fu)) << 16) | ((0x80u | (l & 0x3Fu)) << 24);
+          }
+          t = state;
+          for (uint32_t k = 0; k < nraw; k++) { t = ac_step(A, t & ID_MASK, (enc >> (8 * k)) & 0xFFu); }
+        }
+      }
+      state = t & ID_MASK;
+      if (!(t & OUT_FLAG)) continue;
+      const uint64_t e = p + 1;
+      for (uint32_t ch = __ldg(A.first_out + state); ch != NONE; ch = __ldg(A.next_out + ch)) {
+        const uint32_t olo = __ldg(A.own_off + ch), ohi = __ldg(A.own_off + ch + 1);
+        for (uint32_t o = olo; o < ohi; o++) {
+          const uint32_t rank = __ldg(A.own_rank + o);
+          const uint32_t id = __ldg(A.id_of_rank + rank);
+          if (id <= pass_id) continue;
+          uint64_t s;
+          if (!ignore_case) s = e - __ldg(A.len_of_rank + rank);
+          else { const long long es = skip_back(v, e - 1, (long long)__ldg(&info[id].len_cps) - 1); if (es < 0) { sc->error = 1; continue; } s = (uint64_t)es; }
+          // touches edit j: holds a replacement byte, or (deletion) spans the junction
+          const bool mine = repl_len ? (s < ns + repl_len && e > ns) : (s < ns && e > ns);
+          if (!mine) continue;
+          if (has_next && (repl_len ? (s < ns2 + repl_len && e > ns2) : (s < ns2 && e > ns2))) continue;   // the next edit reports it
+          append_key(out, reinterpret_cast<unsigned long long*>(&sc->n_new), cap, (e << A.rank_bits) | rank);
+        }
+      }
+    }
+  }
+}
+
+// Replacer.runWithLimit (:203-242) on a device-resident text, the reference's literal pass structure: every pass scans the
+// whole text (or, CaseSensitive, carries the match list) and splices into the other ping-pong buffer.  Used for replacers
+// the tiled form below does not take (an empty needle), and with AM_REPLACER_RESCAN=1 as the A/B reference.
+// `d_in` is only read; the result is left in a buffer of the library's: *d_out (cudaMalloc'ed, ownership passes to the
+// caller), *out_len.
+static int replacer_core_classic(const am_replacer* r, const Image* a, int cs, const uint8_t* d_in, uint64_t len, uint64_t max_len, cudaStream_t st,
                          uint8_t** d_out, uint64_t* out_len, int* exceeded) {
   *d_out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0; g_last_rescans = 0;
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
@@ -440,6 +827,257 @@ static int replacer_core(const am_replacer* r, const Image* a, int cs, const uin
   return done(AM_OK);
 }
 
+// IdInfo of every needle id for one case mode (the rank of a needle depends on the image), built on first use.
+static int replacer_idinfo(const am_replacer* cr, const Image* a, int cs, const IdInfo** out) {
+  am_replacer* r = const_cast<am_replacer*>(cr);
+  std::lock_guard<std::mutex> g(r->mu);
+  if (!r->d_idinfo[cs]) {
+    std::vector<IdInfo> h(r->n ? r->n : 1);
+    for (uint64_t i = 0; i < r->n; i++) h[i] = IdInfo{a->host.rank_of_id[i], r->repl_off[i], r->repl_off[i + 1] - r->repl_off[i], r->len_bytes[i], r->len_cps[i]};
+    void* p = nullptr;
+    if (cudaMalloc(&p, h.size() * sizeof(IdInfo)) != cudaSuccess) { cudaGetLastError(); return fail(AM_E_OOM, "cudaMalloc(needle info)"); }
+    cudaError_t e = cudaMemcpy(p, h.data(), h.size() * sizeof(IdInfo), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "needle info"); }
+    r->d_idinfo[cs] = p;
+  }
+  *out = static_cast<const IdInfo*>(r->d_idinfo[cs]);
+  return AM_OK;
+}
+
+// Replacer.runWithLimit (:203-242) with the match list carried between the passes and the text in tiles (see above).
+static int replacer_core_tiled(const am_replacer* r, const Image* a, int cs, const uint8_t* d_in, uint64_t len, uint64_t max_len, cudaStream_t st,
+                               uint8_t** d_out, uint64_t* out_len, int* exceeded) {
+  *d_out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0; g_last_rescans = 0; g_last_replacer_ms = 0.f; g_last_replacer_bytes = 0;
+  Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
+  DevBuf contig, tiles, tile_len, tile_base[2], tile_flag, touched, new_len, sel, starts, ends, keep, kidx, kstart, kend, kdelta, kshift, cubtmp, scal;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool prof = profiling_enabled();
+  int rc;
+  auto done = [&](int code) {
+    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+    release_ws(a, ws); return code;
+  };
+  const IdInfo* d_info = nullptr;
+  if ((rc = replacer_idinfo(r, a, cs, &d_info)) || (rc = scal.ensure(sizeof(PassScalars) + 64))) return done(rc);
+  if (prof) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+  PassScalars* d_sc = scal.as<PassScalars>();
+  PassScalars* h_sc = reinterpret_cast<PassScalars*>(ws->h_scalars + 256);   // pinned
+  const uint32_t rank_bits = a->host.rank_bits;
+  const uint64_t mask = (1ull << rank_bits) - 1;
+  const int ic = cs == AM_IGNORE_CASE;
+  long long prev_id = -1;                          // threshold 1 keeps every priority (:211)
+  const long long last_id = (long long)r->n - 1;   // minPriority = 1 - numNeedles (:217)
+  uint64_t bytes_moved = 0;
+
+  const uint8_t* cur = d_in;                       // the contiguous text (when !tiled)
+  bool tiled = false;
+  uint32_t T = 0; int tb_cur = 0;                  // tiles: count, which tile_base buffer is current
+  auto view = [&]() -> TextView {
+    if (tiled) return TextView{tiles.as<uint8_t>(), len, tile_len.as<uint32_t>(), tile_base[tb_cur].as<uint64_t>(), T, 1u};
+    return TextView{cur, len, nullptr, nullptr, 0u, 0u};
+  };
+  auto scan_tiles = [&](int into) -> int {         // tile_base[into] = exclusive prefix of tile_len (T + 1 entries; tile_len[T] = 0)
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, tile_len.as<uint32_t>(), tile_base[into].as<unsigned long long>(), (int64_t)T + 1, st);
+    { int rc2 = cubtmp.ensure(tb); if (rc2) return rc2; }
+    cudaError_t e2 = cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, tile_len.as<uint32_t>(), tile_base[into].as<unsigned long long>(), (int64_t)T + 1, st);
+    return e2 == cudaSuccess ? AM_OK : cuda_fail(e2, "tile scan");
+  };
+  auto tileify = [&]() -> int {                    // contiguous `cur` -> tiles
+    T = (uint32_t)((len + TILE_FILL - 1) / TILE_FILL); if (T == 0) T = 1;
+    int rc2;
+    if ((rc2 = tiles.ensure((size_t)T * TILE_CAP + 64)) || (rc2 = tile_len.ensure(((size_t)T + 1) * 4)) || (rc2 = tile_base[0].ensure(((size_t)T + 1) * 8)) ||
+        (rc2 = tile_base[1].ensure(((size_t)T + 1) * 8)) || (rc2 = tile_flag.ensure((size_t)T * 4)) || (rc2 = touched.ensure((size_t)T * 4)) || (rc2 = new_len.ensure((size_t)T * 4)))
+      return rc2;
+    cudaMemsetAsync(tile_flag.p, 0, (size_t)T * 4, st);
+    cudaMemsetAsync(tile_len.as<uint32_t>() + T, 0, 4, st);
+    g_kernel_launches++;
+    tileify_kernel<<<std::min<uint32_t>(T, 148 * 16), 128, 0, st>>>(cur, len, tiles.as<uint8_t>(), tile_len.as<uint32_t>(), T);
+    tb_cur = 0;
+    bytes_moved += 2 * len;
+    return scan_tiles(0);
+  };
+  auto materialize = [&](DevBuf* into) -> int {    // tiles -> a contiguous buffer of the library's
+    int rc2 = into->ensure(len + 64);
+    if (rc2) return rc2;
+    g_kernel_launches++;
+    materialize_kernel<<<std::min<uint32_t>(T, 148 * 16), 128, 0, st>>>(tiles.as<uint8_t>(), tile_len.as<uint32_t>(), tile_base[tb_cur].as<uint64_t>(), T, into->as<uint8_t>());
+    bytes_moved += 2 * len;
+    return cudaGetLastError() == cudaSuccess ? AM_OK : cuda_fail(cudaGetLastError(), "materialize");
+  };
+
+  bool have_list = false;
+  uint64_t n = 0;
+  DevBuf spare;                                    // second contiguous buffer of the overflow path
+  DevBuf keys_c, rkeys;                            // the match list ping-pongs between ws->keys_b and keys_c; rkeys: rescanned matches of a pass
+  uint64_t* list = nullptr;                        // the current (sorted) match list
+  uint64_t* other = nullptr;
+  for (;;) {
+    // ---- 1. the matches of the current text: a full scan of the (contiguous) text, or the carried list ------------------------
+    if (!have_list) {
+      if (tiled) {                                 // (only after a pass whose match list outgrew the key buffers)
+        if ((rc = materialize(&contig))) return done(rc);
+        cur = contig.as<uint8_t>(); tiled = false;
+      }
+      am_dev_text t{cur, len, 0, 0};
+      if ((rc = find_all_sorted(a, ws, t, st, &n))) return done(rc);
+      g_last_rescans++;
+      bytes_moved += len;
+      if ((rc = keys_c.ensure(ws->keys_b_bytes))) return done(rc);
+      list = ws->keys_b; other = keys_c.as<uint64_t>();
+    }
+    g_last_passes++;
+    if (n == 0) break;                             // (_, []) -> Just haystack (:230)
+    const uint64_t list_cap = std::min<uint64_t>(ws->keys_b_bytes, keys_c.cap) / 8;
+    // ---- 2. the needle of the pass and its matches: first host round trip (two scalars) ---------------------------------------------
+    if ((rc = sel.ensure(n * 8))) return done(rc);
+    const unsigned gn = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+    g_kernel_launches += 4;
+    pass_begin_kernel<<<1, 1, 0, st>>>(d_sc);
+    best_needle_kernel<<<gn, 256, 0, st>>>(list, n, mask, a->dev.id_of_rank, prev_id, &d_sc->best);
+    pass_resolve_kernel<<<1, 1, 0, st>>>(d_sc, d_info);
+    {
+      size_t tb = 0;
+      RankIsDev pred{mask, d_sc};
+      cub::DeviceSelect::If(nullptr, tb, list, sel.as<uint64_t>(), &d_sc->nsel, (int64_t)n, pred, st);
+      if ((rc = cubtmp.ensure(tb))) return done(rc);
+      cub::DeviceSelect::If(cubtmp.p, tb, list, sel.as<uint64_t>(), &d_sc->nsel, (int64_t)n, pred, st);
+    }
+    cudaMemcpyAsync(h_sc, d_sc, sizeof(PassScalars), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(cuda_fail(e, "replacer pass"));
+    if (h_sc->best == NONE) break;                 // nothing below the threshold
+    const uint32_t id = h_sc->best;
+    const uint64_t ns = h_sc->nsel;
+    bytes_moved += n * 8 * 2;
+    // ---- 3..7: the rest of the pass is queued; the second round trip reads its scalars --------------------------------------------------
+    if ((rc = starts.ensure(ns * 8)) || (rc = ends.ensure(ns * 8)) || (rc = keep.ensure(ns + 16)) || (rc = kidx.ensure((ns + 1) * 8)) ||
+        (rc = kstart.ensure(ns * 8 + 8)) || (rc = kend.ensure(ns * 8 + 8)) || (rc = kdelta.ensure((ns + 1) * 8)) || (rc = kshift.ensure((ns + 1) * 8)))
+      return done(rc);
+    const uint64_t rcap = std::max<uint64_t>(1 << 16, 4 * ns * (a->host.halo_bytes + 2));   // rescanned matches: a few per edit at most (overflow: the next pass scans)
+    if ((rc = rkeys.ensure(std::min<uint64_t>(rcap, list_cap) * 8))) return done(rc);
+    const uint64_t rkeys_cap = rkeys.cap / 8;
+    const unsigned gs = (unsigned)std::min<uint64_t>((ns + 127) / 128, 148 * 8);
+    {
+      size_t tb2 = 0, tb3 = 0, tb4 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb2, keep.as<uint8_t>(), kidx.as<uint64_t>(), (int64_t)ns + 1, st);
+      cub::DeviceScan::ExclusiveSum(nullptr, tb3, kdelta.as<long long>(), kshift.as<long long>(), (int64_t)ns + 1, st);
+      cub::DeviceSelect::If(nullptr, tb4, other, other, &d_sc->n_carried, (int64_t)n, NotDropped(), st);
+      if ((rc = cubtmp.ensure(std::max(std::max(tb2, tb3), tb4)))) return done(rc);
+      TextView v = view();
+      g_kernel_launches += 6;
+      starts_view_kernel<<<gs, 128, 0, st>>>(sel.as<uint64_t>(), d_sc, rank_bits, v, ic, starts.as<uint64_t>(), ends.as<uint64_t>(), d_sc);
+      cudaMemsetAsync(keep.p, 0, ns + 16, st);
+      cudaMemsetAsync(kdelta.p, 0, (ns + 1) * 8, st);
+      overlap_dev_kernel<<<gs, 256, 0, st>>>(starts.as<uint64_t>(), ends.as<uint64_t>(), d_sc, keep.as<uint8_t>());
+      cub::DeviceScan::ExclusiveSum(cubtmp.p, tb2, keep.as<uint8_t>(), kidx.as<uint64_t>(), (int64_t)ns + 1, st);               // kidx[ns] = #kept
+      gather_kept_dev_kernel<<<gs, 256, 0, st>>>(starts.as<uint64_t>(), ends.as<uint64_t>(), keep.as<uint8_t>(), kidx.as<uint64_t>(), ns, d_sc,
+                                                 kstart.as<uint64_t>(), kend.as<uint64_t>(), kdelta.as<long long>());
+      cub::DeviceScan::ExclusiveSum(cubtmp.p, tb3, kdelta.as<long long>(), kshift.as<long long>(), (int64_t)ns + 1, st);          // kshift[ns] = total shift
+      total_shift_kernel<<<1, 1, 0, st>>>(kshift.as<long long>(), ns, d_sc);
+      // the next pass's list, part (a): on the text as it still is.  Transformed in place order (into sel's space: n keys),
+      // then compacted into the other list buffer -- still sorted.
+      carry_view_kernel<<<gn, 256, 0, st>>>(list, n, rank_bits, a->dev.id_of_rank, a->dev.len_of_rank, d_info, ic, v, kstart.as<uint64_t>(), kend.as<uint64_t>(),
+                                            kshift.as<long long>(), ns, d_sc, sel.as<uint64_t>());
+      cub::DeviceSelect::If(cubtmp.p, tb4, sel.as<uint64_t>(), other, &d_sc->n_carried, (int64_t)n, NotDropped(), st);
+    }
+    bytes_moved += n * 8 * 4;
+    // the text: rewrite the touched tiles in place
+    if (!tiled) { if ((rc = tileify())) return done(rc); tiled = true; }
+    {
+      TextView v = view();
+      g_kernel_launches += 4;
+      tile_mark_kernel<<<gs, 128, 0, st>>>(d_sc, kstart.as<uint64_t>(), kend.as<uint64_t>(), v, tile_flag.as<uint32_t>(), touched.as<uint32_t>(), d_sc);
+      tile_plan_kernel<<<gs, 128, 0, st>>>(d_sc, touched.as<uint32_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), v, new_len.as<uint32_t>());
+      const unsigned gt = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, std::min<uint64_t>(2 * ns + 1, T)), 148 * 16);
+      tile_splice_kernel<<<gt, 128, 0, st>>>(d_sc, touched.as<uint32_t>(), new_len.as<uint32_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), tiles.as<uint8_t>(),
+                                             tile_len.as<uint32_t>(), tile_base[tb_cur].as<uint64_t>(), tile_flag.as<uint32_t>(), r->d_repl);
+      if ((rc = scan_tiles(tb_cur ^ 1))) return done(rc);
+      // part (b): the neighbourhood of every edit, on the rewritten tiles (the host does not know the new length yet: the kernel
+      // takes it from the new prefix sums)
+      TextView vn{tiles.as<uint8_t>(), 0, tile_len.as<uint32_t>(), tile_base[tb_cur ^ 1].as<uint64_t>(), T, 1u};
+      const unsigned gk = (unsigned)std::min<uint64_t>((ns + 63) / 64, 148 * 16);
+      rescan_view_kernel<<<gk, 64, 0, st>>>(a->dev, vn, d_info, ic, kstart.as<uint64_t>(), kshift.as<long long>(), d_sc, rkeys.as<uint64_t>(), rkeys_cap);
+    }
+    // ---- the second host round trip of the pass -------------------------------------------------------------------------------------------
+    cudaMemcpyAsync(h_sc, d_sc, sizeof(PassScalars), cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(cuda_fail(e, "replacer pass"));
+    if (h_sc->error) return done(fail(AM_E_BADARG, "Invalid use of skipCodePointsBackwards (text is not valid UTF-8?)"));
+    if (max_len != UINT64_MAX) {                   // replacementLength over the un-deoverlapped matches (:240)
+      const long long would = (long long)len + h_sc->delta_sum;
+      if (would > 0 && (uint64_t)would > max_len) { *exceeded = 1; return done(AM_OK); }
+    }
+    const uint64_t K = h_sc->nkept;
+    const uint64_t new_len_total = (uint64_t)((long long)len + h_sc->total_shift);
+    bytes_moved += (uint64_t)h_sc->ntouched * 2 * TILE_FILL + K * (2 * a->host.halo_bytes + h_sc->id.repl_len);
+    have_list = false;
+    if (h_sc->overflow) {
+      // a tile would have outgrown its slot: this pass splices the contiguous way, the next one cuts new tiles
+      if ((rc = materialize(&contig))) return done(rc);
+      if ((rc = spare.ensure(new_len_total + 64))) return done(rc);
+      uint64_t tl = (len + SPLICE_TILE - 1) / SPLICE_TILE; if (tl == 0) tl = 1;
+      g_kernel_launches++;
+      splice_kernel<<<(unsigned)tl, 256, 0, st>>>(contig.as<uint8_t>(), len, spare.as<uint8_t>(), kstart.as<uint64_t>(), kend.as<uint64_t>(), kshift.as<long long>(), K,
+                                                  r->d_repl + h_sc->id.repl_off, h_sc->id.repl_len, h_sc->total_shift);
+      if ((e = cudaGetLastError()) != cudaSuccess) return done(cuda_fail(e, "splice launch"));
+      std::swap(contig.p, spare.p); std::swap(contig.cap, spare.cap);
+      cur = contig.as<uint8_t>(); tiled = false;
+      bytes_moved += len + new_len_total;
+      len = new_len_total;                         // (the carried list lacks part (b): the next pass scans)
+    } else {
+      tb_cur ^= 1;
+      len = new_len_total;
+      const uint64_t nA = h_sc->n_carried, nB = h_sc->n_new;
+      if (nB <= rkeys_cap && nA + nB <= list_cap) {
+        if (nB == 0) std::swap(list, other);       // the compacted carried list IS the next pass's list
+        else {
+          // sort the few rescanned matches, merge them into the carried list (into the buffer the old list occupied)
+          const int end_bit = std::min(64, bitlen(len) + (int)rank_bits);
+          size_t stb = sort_temp_bytes(nB, end_bit);
+          if ((rc = ws->need_sort_temp(stb)) || (rc = sel.ensure(nB * 8))) return done(rc);
+          if ((e = sort_keys(ws->sort_temp, stb, rkeys.as<uint64_t>(), sel.as<uint64_t>(), nB, end_bit, st)) != cudaSuccess) return done(cuda_fail(e, "radix sort"));
+          g_kernel_launches++;
+          merge_kernel<<<(unsigned)std::min<uint64_t>((nA + nB + 255) / 256, 148 * 8), 256, 0, st>>>(other, nA, sel.as<uint64_t>(), nB, list);
+          bytes_moved += (nA + nB) * 8 * 2;
+        }
+        n = nA + nB;
+        have_list = true;
+      }                                            // (else: more matches than the buffers hold -- the next pass scans, which resizes them)
+    }
+    if ((long long)id == last_id) break;           // p == minPriority: no needle is left (:241)
+    prev_id = id;                                   // go p (:242)
+  }
+  // ---- the result: a contiguous buffer of the library's ----------------------------------------------------------------------------------
+  DevBuf result;
+  if (tiled) { if ((rc = materialize(&result))) return done(rc); }
+  else if (cur == contig.p && contig.p) { std::swap(result.p, contig.p); std::swap(result.cap, contig.cap); }
+  else {
+    if ((rc = result.ensure(len + 64))) return done(rc);
+    if (len && cudaMemcpyAsync(result.p, cur, len, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return done(cuda_fail(cudaGetLastError(), "result copy"));
+    bytes_moved += 2 * len;
+  }
+  if (prof) cudaEventRecord(ev1, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(cuda_fail(e, "replacer"));
+  if (prof) cudaEventElapsedTime(&g_last_replacer_ms, ev0, ev1);
+  g_last_replacer_bytes = bytes_moved;
+  *d_out = result.as<uint8_t>(); result.p = nullptr; result.cap = 0;
+  *out_len = len;
+  return done(AM_OK);
+}
+
+// The form a run takes: tiles + carried match list unless the replacer holds an empty needle (its matches have no span to
+// carry), its stored needles and payload lengths disagree in a CaseSensitive run (a replacer switched to the other case
+// mode after `build`), a needle is longer than a quarter tile, or AM_REPLACER_RESCAN=1 asks for the reference's literal form.
+static int replacer_core(const am_replacer* r, const Image* a, int cs, const uint8_t* d_in, uint64_t len, uint64_t max_len, cudaStream_t st,
+                         uint8_t** d_out, uint64_t* out_len, int* exceeded) {
+  const char* env_rescan = std::getenv("AM_REPLACER_RESCAN");   // read per call so that tests can A/B both forms
+  const bool force_rescan = env_rescan && std::atoi(env_rescan) != 0;
+  const bool ok = !r->has_empty && !(cs == AM_CASE_SENSITIVE && r->stored_len_differs) && a->host.max_len <= TILE_FILL / 4 && a->host.halo_bytes <= TILE_FILL / 4;
+  if (ok && !force_rescan) return replacer_core_tiled(r, a, cs, d_in, len, max_len, st, d_out, out_len, exceeded);
+  return replacer_core_classic(r, a, cs, d_in, len, max_len, st, d_out, out_len, exceeded);
+}
+
 extern "C" {
 
 void am_replacer_free(am_replacer* r);
@@ -521,6 +1159,7 @@ void am_replacer_free(am_replacer* r) {
     DeviceGuard g;
     if (r->automaton && r->automaton->device >= 0) g.enter(r->automaton->device);
     cudaFree(r->d_repl);
+    for (void* p : r->d_idinfo) if (p) cudaFree(p);
   }
   if (r->automaton) am_automaton_free(r->automaton);
   delete r;
@@ -537,6 +1176,7 @@ static int replacer_enter(const am_replacer* r, int cs, Image** im, DeviceGuard*
 
 int am_replacer_run_dev(const am_replacer* r, int cs, const void* dev_text, uint64_t text_len, uint64_t max_len, void* stream, void** dev_out,
                         uint64_t* out_len, int* exceeded) {
+  AM_NVTX("am_replacer_run_dev");
   if (!dev_out || !out_len || !exceeded) return fail(AM_E_BADARG, "null argument");
   if (text_len > 0 && !dev_text) return fail(AM_E_BADARG, "dev_text is null");
   Image* im = nullptr; DeviceGuard guard;
@@ -548,6 +1188,7 @@ int am_replacer_run_dev(const am_replacer* r, int cs, const void* dev_text, uint
 }
 
 int am_replacer_run(const am_replacer* r, int cs, const am_u8slice* hay, uint64_t max_len, uint8_t** out, uint64_t* out_len, int* exceeded) {
+  AM_NVTX("am_replacer_run");
   if (!out || !out_len || !exceeded || !hay) return fail(AM_E_BADARG, "null argument");
   if (hay->len < 0 || hay->off < 0 || (hay->len > 0 && !hay->ptr)) return fail(AM_E_BADARG, "bad text slice");
   Image* im = nullptr; DeviceGuard guard;

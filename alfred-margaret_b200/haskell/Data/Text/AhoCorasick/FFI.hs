@@ -1,25 +1,40 @@
+{-# LANGUAGE BangPatterns #-}
 {-# LANGUAGE ForeignFunctionInterface #-}
--- | Raw bindings to libam_b200.so (include/am_b200.h).
+{-# LANGUAGE MagicHash #-}
+-- | Raw bindings to libam_b200.so (include/am_b200.h, ABI version 2) and the marshalling helpers every wrapper
+-- module uses.
 --
 -- NOT COMPILED IN THIS REPOSITORY: GHC is not available in the build image.  This is the shim a maintainer
 -- of alfred-margaret would add; it follows the reference's own FFI precedent,
--- benchmark/rust-ffi/app/Main.hs:28-52 (`U8Slice`, pinned arrays, `ccall`).
--- Long GPU calls use `ccall safe` so other Haskell threads keep running.
+-- benchmark/rust-ffi/app/Main.hs:28-52: `Ptr U8Slice` arguments over pinned arrays, plain integers back.
+-- Every struct of the header travels by pointer, so no C glue is needed (GHC's FFI cannot pass structs by value).
+-- Long GPU calls are `ccall safe` so other Haskell threads keep running; the error text is thread-local in the
+-- library, so a failed call and the read of its message are bound to one OS thread (`amCall`).
 module Data.Text.AhoCorasick.FFI
   ( U8Slice (..), AmMatch (..), AmLowerPair (..)
   , AmAutomaton, AmReplacer
-  , c_am_automaton_build, c_am_automaton_free_ptr
+  , c_am_automaton_build, c_am_automaton_free_ptr, c_am_automaton_prepare
   , c_am_contains_any, c_am_count_matches, c_am_find_all, c_am_contains_all
-  , c_am_replacer_build, c_am_replacer_free_ptr, c_am_replacer_run, c_am_free
-  , c_am_last_error
+  , c_am_replacer_build, c_am_replacer_build_stored, c_am_replacer_free_ptr, c_am_replacer_run, c_am_free
   , amOk, amEOverflow
+  , caseToC, toSlice, withSlice, withSlices, withLowerTable, amCall, pinText
   ) where
 
+import Control.Concurrent (runInBoundThread)
+import Control.Monad (when)
+import Data.Text.CaseSensitivity (CaseSensitivity (..))
+import Data.Text.Utf8 (Text (..))
 import Data.Word (Word8, Word32, Word64)
-import Foreign.C.String (CString)
-import Foreign.C.Types (CInt (..), CSize (..))
-import Foreign.Ptr (FunPtr, Ptr)
+import Foreign.C.String (peekCString)
+import Foreign.C.Types (CChar, CInt (..), CSize (..))
+import Foreign.Marshal (alloca, allocaBytes, withArrayLen)
+import Foreign.Ptr (FunPtr, Ptr, castPtr, nullPtr)
 import Foreign.Storable (Storable (..))
+import System.IO.Unsafe (unsafePerformIO)
+
+import qualified Data.Char as Char
+import qualified Data.Text.Array as TextArray
+import qualified Data.Text.Utf8 as Utf8
 
 -- | `am_u8slice`: an unpacked `Text u8data off len`; the array must be pinned
 -- (Utf8.isArrayPinned / arrayContents, src/Data/Text/Utf8.hs:325-331).
@@ -56,29 +71,95 @@ amOk, amEOverflow :: CInt
 amOk = 0
 amEOverflow = 4
 
--- struct am_lower_table { const am_lower_pair* pairs; size_t n; } and struct am_options are passed by pointer
--- (Ptr ()) from small `alloca`'d buffers in the wrapper modules.
+-- | `AM_CASE_SENSITIVE = 0`, `AM_IGNORE_CASE = 1` (Data.Text.CaseSensitivity, :14-16).
+caseToC :: CaseSensitivity -> CInt
+caseToC CaseSensitive = 0
+caseToC IgnoreCase = 1
+
+-- struct am_lower_table { const am_lower_pair* pairs; size_t n; } and struct am_options travel by pointer (Ptr ()).
 foreign import ccall safe "am_automaton_build"
-  c_am_automaton_build :: Ptr U8Slice -> CSize -> CInt -> Ptr () -> Ptr () -> Ptr (Ptr AmAutomaton) -> IO CInt
+  c_am_automaton_build :: Ptr U8Slice -> CSize -> Ptr () -> Ptr () -> Ptr (Ptr AmAutomaton) -> IO CInt
 foreign import ccall "&am_automaton_free"
   c_am_automaton_free_ptr :: FunPtr (Ptr AmAutomaton -> IO ())
--- U8Slice is passed BY VALUE in the C ABI (24 bytes => in memory on SysV x86-64); GHC's FFI cannot pass structs by
--- value, so the shim links a 10-line C file (am_shim.c, see INTEGRATION.md) that takes `const am_u8slice*`.
-foreign import ccall safe "am_shim_contains_any"
-  c_am_contains_any :: Ptr AmAutomaton -> Ptr U8Slice -> Ptr CInt -> IO CInt
-foreign import ccall safe "am_shim_count_matches"
-  c_am_count_matches :: Ptr AmAutomaton -> Ptr U8Slice -> Ptr Word64 -> IO CInt
-foreign import ccall safe "am_shim_find_all"
-  c_am_find_all :: Ptr AmAutomaton -> Ptr U8Slice -> Ptr AmMatch -> CSize -> Ptr Word64 -> IO CInt
-foreign import ccall safe "am_shim_contains_all"
-  c_am_contains_all :: Ptr AmAutomaton -> Ptr U8Slice -> Ptr CInt -> IO CInt
+foreign import ccall safe "am_automaton_prepare"
+  c_am_automaton_prepare :: Ptr AmAutomaton -> CInt -> IO CInt
+foreign import ccall safe "am_contains_any"
+  c_am_contains_any :: Ptr AmAutomaton -> CInt -> Ptr U8Slice -> Ptr CInt -> IO CInt
+foreign import ccall safe "am_count_matches"
+  c_am_count_matches :: Ptr AmAutomaton -> CInt -> Ptr U8Slice -> Ptr Word64 -> IO CInt
+foreign import ccall safe "am_find_all"
+  c_am_find_all :: Ptr AmAutomaton -> CInt -> Ptr U8Slice -> Ptr AmMatch -> CSize -> Ptr Word64 -> IO CInt
+foreign import ccall safe "am_contains_all"
+  c_am_contains_all :: Ptr AmAutomaton -> CInt -> Ptr U8Slice -> Ptr CInt -> IO CInt
 foreign import ccall safe "am_replacer_build"
   c_am_replacer_build :: Ptr U8Slice -> Ptr U8Slice -> CSize -> CInt -> Ptr () -> Ptr () -> Ptr (Ptr AmReplacer) -> IO CInt
+foreign import ccall safe "am_replacer_build_stored"
+  c_am_replacer_build_stored :: Ptr U8Slice -> Ptr Word32 -> Ptr Word32 -> Ptr U8Slice -> CSize -> CInt -> Ptr () -> Ptr () -> Ptr (Ptr AmReplacer) -> IO CInt
 foreign import ccall "&am_replacer_free"
   c_am_replacer_free_ptr :: FunPtr (Ptr AmReplacer -> IO ())
-foreign import ccall safe "am_shim_replacer_run"
-  c_am_replacer_run :: Ptr AmReplacer -> Ptr U8Slice -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> Ptr CInt -> IO CInt
+foreign import ccall safe "am_replacer_run"
+  c_am_replacer_run :: Ptr AmReplacer -> CInt -> Ptr U8Slice -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> Ptr CInt -> IO CInt
 foreign import ccall unsafe "am_free"
   c_am_free :: Ptr a -> IO ()
-foreign import ccall unsafe "am_last_error"
-  c_am_last_error :: IO CString
+foreign import ccall unsafe "am_last_error_copy"
+  c_am_last_error_copy :: Ptr CChar -> CSize -> IO CSize
+
+-- | Run an ABI call and turn a non-zero status (other than the ones in `allowed`) into `error` with the library's
+-- message.  The reference has no error channel on this path (its functions are total on valid input), so a failure
+-- here -- no device, out of memory -- is exceptional.  Call and message read share one OS thread.
+amCall :: String -> [CInt] -> IO CInt -> IO CInt
+amCall what allowed act = runInBoundThread $ do
+  rc <- act
+  when (rc /= amOk && rc `notElem` allowed) $ do
+    msg <- allocaBytes 512 $ \buf -> c_am_last_error_copy buf 512 >> peekCString buf
+    error (what ++ ": libam_b200 status " ++ show rc ++ ": " ++ msg)
+  pure rc
+
+-- | A Text whose array is pinned, so that its address may cross the FFI (Utf8.isArrayPinned, Utf8.hs:325-328).  GHC
+-- pins large arrays (>= ~3 KiB) itself; a small unpinned one is copied once into a pinned array, as the reference's
+-- benchmark does with `compact` (benchmark/rust-ffi/app/Main.hs:75).
+pinText :: Text -> Text
+pinText t@(Text u8data off len)
+  | Utf8.isArrayPinned u8data = t
+  | otherwise = Text (TextArray.run (do { dst <- TextArray.newPinned len; TextArray.copyI len dst 0 u8data off; pure dst })) 0 len
+
+-- | `U8Slice` of a PINNED Text (the reference's `fromText`, benchmark/rust-ffi/app/Main.hs:49-52).
+toSlice :: Text -> U8Slice
+toSlice (Text u8data off len)
+  | Utf8.isArrayPinned u8data = U8Slice (Utf8.arrayContents u8data) off len
+  | otherwise                 = error "ByteArray is not pinned"
+
+-- | Pin if needed, write the slice to a temporary and keep the array alive across the call.
+withSlice :: Text -> (Ptr U8Slice -> IO a) -> IO a
+withSlice text act =
+  let !pinned@(Text arr _ _) = pinText text
+  in alloca $ \p -> do
+       poke p (toSlice pinned)
+       r <- act p
+       TextArray.touch arr      -- keeps the ByteArray# alive until the call has returned (Data.Text.Array)
+       pure r
+
+-- | An array of slices (needles, replacements).
+withSlices :: [Text] -> (Ptr U8Slice -> CSize -> IO a) -> IO a
+withSlices texts act =
+  let pinned = map pinText texts
+  in withArrayLen (map toSlice pinned) $ \n p -> do
+       r <- act p (fromIntegral n)
+       mapM_ (\(Text arr _ _) -> TextArray.touch arr) pinned
+       pure r
+
+-- | The host's `Data.Char.toLower` above ASCII as data (Utf8.lowerCodePoint, Utf8.hs:145-151, is `Char.toLower` there):
+-- the table depends on the GHC that compiles the host (Unicode version of `base`), so it is enumerated here, once.
+lowerPairs :: [AmLowerPair]
+lowerPairs = [ AmLowerPair (fromIntegral (Char.ord c)) (fromIntegral (Char.ord l))
+             | c <- ['\x80' .. maxBound], let l = Char.toLower c, l /= c ]
+{-# NOINLINE lowerPairs #-}
+
+-- | Pass `am_lower_table { pairs, n }` by pointer.
+withLowerTable :: (Ptr () -> IO a) -> IO a
+withLowerTable act =
+  withArrayLen lowerPairs $ \n pairs ->
+  allocaBytes 16 $ \tbl -> do
+    pokeByteOff tbl 0 pairs
+    pokeByteOff tbl 8 (fromIntegral n :: Word64)
+    act (castPtr tbl)

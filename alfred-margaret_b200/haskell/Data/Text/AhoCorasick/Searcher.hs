@@ -26,8 +26,8 @@ data Searcher v = Searcher                         -- Searcher.hs:61-66
 build :: CaseSensitivity -> [Text] -> Searcher ()                                   -- :110-111
 build case_ = buildWithValues case_ . fmap (\n -> (n, ()))
 
-buildWithValues :: Hashable v => CaseSensitivity -> [(Text, v)] -> Searcher v      -- :115-118
-buildWithValues case_ ns = Searcher case_ ns (length ns) (Aho.buildWithCase case_ ns)
+buildWithValues :: Hashable v => CaseSensitivity -> [(Text, v)] -> Searcher v      -- :115-118 (IgnoreCase: the caller lower-cases, :107-109)
+buildWithValues case_ ns = Searcher case_ ns (length ns) (Aho.build ns)
 
 buildNeedleIdSearcher :: CaseSensitivity -> [Text] -> Searcher Int                 -- :167-169
 buildNeedleIdSearcher case_ ns = buildWithValues case_ (zip ns [0 ..])
@@ -41,22 +41,26 @@ automaton = searcherAutomaton
 caseSensitivity :: Searcher v -> CaseSensitivity
 caseSensitivity = searcherCaseSensitive
 
-setCaseSensitivity :: CaseSensitivity -> Searcher v -> Searcher v                   -- :142-145 (rebuilds the device image)
-setCaseSensitivity case_ s = s { searcherCaseSensitive = case_, searcherAutomaton = Aho.buildWithCase case_ (searcherNeedles s) }
+-- | :142-145: flips the flag; needles and automaton are shared -- the machine serves both modes, nothing is rebuilt.
+setCaseSensitivity :: CaseSensitivity -> Searcher v -> Searcher v
+setCaseSensitivity case_ s = s { searcherCaseSensitive = case_ }
 
 mapSearcher :: (a -> b) -> Searcher a -> Searcher b                                 -- :121-125 (payloads live on the host)
 mapSearcher f s = s { searcherNeedles = fmap (fmap f) (searcherNeedles s), searcherAutomaton = fmap f (searcherAutomaton s) }
 
--- | `containsAny` (:156-164): one am_contains_any call (the kernel sets a flag; other CTAs stop at the next tile).
+-- | `containsAny` (:156-164): one am_contains_any call.  The kernel sets a flag at the first match, the other CTAs
+-- stop at their next tile and the upload of the haystack stops with them: the fold's `Done True`.
 containsAny :: Searcher () -> Text -> Bool
 containsAny s text = unsafePerformIO $ withForeignPtr (Aho.machineHandle (automaton s)) $ \h ->
-  Aho.withSlice text $ \hay -> alloca $ \out -> do
-    rc <- c_am_contains_any h hay out
-    if rc /= amOk then Aho.amError "am_contains_any" else (/= 0) <$> peek out
+  withSlice text $ \hay -> alloca $ \out -> do
+    _ <- amCall "am_contains_any" [] $ c_am_contains_any h (caseToC (caseSensitivity s)) hay out
+    (/= 0) <$> peek out
+{-# NOINLINE containsAny #-}
 
--- | `containsAll` (:173-187).
+-- | `containsAll` (:173-187), for searchers from `buildNeedleIdSearcher`: a bit per needle on the device.
 containsAll :: Searcher Int -> Text -> Bool
 containsAll s text = unsafePerformIO $ withForeignPtr (Aho.machineHandle (automaton s)) $ \h ->
-  Aho.withSlice text $ \hay -> alloca $ \out -> do
-    rc <- c_am_contains_all h hay out
-    if rc /= amOk then Aho.amError "am_contains_all" else (/= 0) <$> peek out
+  withSlice text $ \hay -> alloca $ \out -> do
+    _ <- amCall "am_contains_all" [] $ c_am_contains_all h (caseToC (caseSensitivity s)) hay out
+    (/= 0) <$> peek out
+{-# NOINLINE containsAll #-}
