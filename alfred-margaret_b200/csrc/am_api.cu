@@ -63,7 +63,7 @@ static int upload(Image* a, const std::vector<T>& v, const T** out) {
 }
 
 Workspace::~Workspace() {
-  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases, (void*)seen_bits, (void*)surv})
+  for (void* p : {(void*)d_scalars, (void*)keys_a, (void*)keys_b, sort_temp, (void*)text, (void*)matches, (void*)aux_a, (void*)aux_b, (void*)seg_counts, (void*)seg_bases, (void*)seen_bits, (void*)surv, (void*)surv_counts})
     if (p) cudaFree(p);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -113,7 +113,8 @@ Image::~Image() {
   for (void* p : dev_allocs) cudaFree(p);
 }
 
-constexpr size_t SCALARS_BYTES = 1024;   // d_scalars / h_scalars: [0..64) scan counters, [64..) the gathered per-rank counts of the sharded calls
+constexpr size_t SCALARS_BYTES = 1024;
+constexpr uint32_t SURV_REGIONS_MAX = 1024;   // per-CTA regions of the survivor list (one per SM in use)   // d_scalars / h_scalars: [0..64) scan counters, [64..) the gathered per-rank counts of the sharded calls
 
 Workspace* acquire_ws(const Image* ca) {
   Image* a = const_cast<Image*>(ca);
@@ -122,7 +123,8 @@ Workspace* acquire_ws(const Image* ca) {
     if (!a->ws_pool.empty()) { Workspace* w = a->ws_pool.back(); a->ws_pool.pop_back(); return w; }
   }
   Workspace* w = new Workspace();
-  if (cudaMalloc((void**)&w->d_scalars, SCALARS_BYTES) != cudaSuccess || cudaMallocHost((void**)&w->h_scalars, SCALARS_BYTES) != cudaSuccess) {
+  if (cudaMalloc((void**)&w->d_scalars, SCALARS_BYTES) != cudaSuccess || cudaMallocHost((void**)&w->h_scalars, SCALARS_BYTES) != cudaSuccess ||
+      cudaMalloc((void**)&w->surv_counts, SURV_REGIONS_MAX * 8) != cudaSuccess) {
     cudaGetLastError(); delete w; return nullptr;
   }
   return w;
@@ -154,12 +156,15 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
   sa.d_flag = reinterpret_cast<int*>(ws->d_scalars + 8);
   sa.d_keys = ws->keys_a; sa.cap = ws->keys_a_bytes / 8;
   static const uint32_t dbg = []() { const char* e = std::getenv("AM_DEBUG_FLAGS"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+  static const uint32_t force_list = []() { const char* e = std::getenv("AM_FILTER_LIST"); return e ? (uint32_t)std::atoi(e) : 0u; }();
+  sa.force_list = force_list;
   sa.debug = dbg; sa.krow = 4u * (uint32_t)filter_copies(a->dev.q, a->dev.t2_exact != 0);
   cudaError_t e = cudaMemsetAsync(ws->d_scalars, 0, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   // filter scan: the survivor list between filter_kernel and verify_kernel.  1 / 256 of the positions to begin with (C2: 1 / 2000
   // survive); a scan that produces more is repeated with the list grown to what it asked for (scan_overflowed).
-  sa.surv = nullptr; sa.surv_count = reinterpret_cast<unsigned long long*>(ws->d_scalars + 48); sa.surv_cap = 0; sa.any_mode = mode == MODE_ANY;
+  sa.surv = nullptr; sa.surv_counts = ws->surv_counts; sa.surv_count = reinterpret_cast<unsigned long long*>(ws->d_scalars + 48); sa.surv_cap_cta = 0; sa.any_mode = mode == MODE_ANY;
+  sa.surv_regions = std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX);
   ws->last_span = t.text_len - std::min(t.report_begin, t.text_len);
   Image* am = const_cast<Image*>(a);
   const unsigned scan_no = am->scans.fetch_add(1, std::memory_order_relaxed);
@@ -169,9 +174,10 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
     const uint64_t span = ws->last_span;
     int rc = ws->need_surv(std::max<uint64_t>(1u << 16, span / 256));
     if (rc) return rc;
-    sa.surv = ws->surv; sa.surv_cap = ws->surv_bytes / 16;
-    if ((e = cudaMemsetAsync(ws->d_scalars + 48, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    sa.surv = ws->surv; sa.surv_cap_cta = ws->surv_bytes / 16 / sa.surv_regions;
+    if ((e = cudaMemsetAsync(ws->surv_counts, 0, (size_t)sa.surv_regions * 8, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
   }
+  if ((e = cudaMemsetAsync(ws->d_scalars + 48, 0, 16, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");   // the survivor counts
   // EMIT on the filter kernel: keys go into per-segment slots of keys_a (first half) + an overflow area (second half)
   ws->emit_segmented = false;
   sa.seg_counts = nullptr; sa.seg_shift = SEG_SHIFT; sa.seg_cap = 0; sa.ovf_base = 0; sa.ovf_cap = 0;
@@ -196,6 +202,7 @@ int launch_scan(const Image* a, Workspace* ws, const am_dev_text& t, int mode, c
     cudaEventRecord(g_ev0, st);
   }
   ws->last_kernel = use_filter ? 2 : 1;
+  ws->last_inline = use_filter && !a->dev.ignore_case && a->dev.q >= 1 && a->dev.q <= 4 && !sa.force_list;   // (the predicate of launch_filter)
   if (use_filter && a->host.case_sensitivity == AM_IGNORE_CASE && t.text_len > 0) {
     // runLower on the filter kernel.  ONE pass over the original text: the probe and the second level work on folded
     // bytes (every byte | 0x20; the cells hold every case variant of the needles' first code points: no `Char.toLower`
@@ -244,11 +251,21 @@ int scan_sync(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cud
 
 // After read_scalars: did the last filter scan produce more survivors than its list holds?  Then its results are incomplete:
 // grow the list to what the scan asked for and tell the caller to repeat it.
-int scan_overflowed(Workspace* ws, bool* again) {
+int scan_overflowed(const Image* a, Workspace* ws, bool* again) {
   *again = false;
-  const uint64_t want = *reinterpret_cast<const uint64_t*>(ws->h_scalars + 48);
-  if (ws->surv == nullptr || want <= ws->surv_bytes / 16) return AM_OK;
-  *again = true;
+  Image* am = const_cast<Image*>(a);
+  if (ws->last_kernel != 2) return AM_OK;
+  const uint64_t want = *reinterpret_cast<const uint64_t*>(ws->h_scalars + 48), total = *reinterpret_cast<const uint64_t*>(ws->h_scalars + 56);
+  if (total * 16 > ws->last_span && ws->last_span >= (1u << 16)) {
+    // a survivor flood: this text defeats the filter.  Hand the scan over to the per-segment walk (and remember it).
+    am->walk_streak.fetch_add(1, std::memory_order_relaxed);
+    if (!ws->last_inline) { ws->force_walk = true; *again = true; }   // (the inline form has verified everything itself: its results stand)
+    return AM_OK;
+  }
+  am->walk_streak.store(0, std::memory_order_relaxed);
+  const uint64_t regions = std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX);
+  if (ws->last_inline || ws->surv == nullptr || want <= ws->surv_bytes / 16 / regions * regions) return AM_OK;
+  *again = true;                                   // some CTA's region was too short: grow the list to regions * (the fullest region) and a quarter
   return ws->need_surv(want + want / 4);
 }
 
@@ -259,7 +276,7 @@ int scan_sync(const Image* a, Workspace* ws, const am_dev_text& t, int mode, cud
     if (rc) return rc;
     if (mode == MODE_ANY && *reinterpret_cast<int*>(ws->h_scalars + 8) != 0) return AM_OK;   // a match is a match, however many survivors went unlisted
     bool again = false;
-    if ((rc = scan_overflowed(ws, &again))) return rc;
+    if ((rc = scan_overflowed(a, ws, &again))) return rc;
     if (!again) return AM_OK;
     if (attempt >= 3) return fail(AM_E_INTERNAL, "survivor count kept growing");
   }
@@ -311,7 +328,7 @@ int emit_finish(const Image* a, Workspace* ws, const am_dev_text& t, cudaStream_
   for (int attempt = 0;; attempt++) {
     const uint64_t cap = ws->keys_a_bytes / 8;
     bool again = false;
-    if ((rc = scan_overflowed(ws, &again))) return rc;
+    if ((rc = scan_overflowed(a, ws, &again))) return rc;
     if (again) {                                   // the survivor list was too short: the keys are incomplete; scan again (the list has grown)
       if (attempt >= 3) return fail(AM_E_INTERNAL, "survivor count kept growing");
       if ((rc = emit_enqueue(a, ws, t, st, matches, matches_cap))) return rc;
@@ -714,12 +731,12 @@ int am_find_all_dev(const am_automaton* a, int cs, const am_dev_text* t, void* s
 // are then incomplete).  Every rank sees every value, so all of them take the same decision: repeat the round (the rank
 // concerned has grown its list) until no flag is raised -- no rank is ever alone in a collective.
 constexpr uint64_t SHARD_RETRY = 1ull << 63;
-static bool shard_round_done(const am_comm* c, Workspace* ws, int* rc) {
+static bool shard_round_done(const Image* a, const am_comm* c, Workspace* ws, int* rc) {
   const uint64_t* g = reinterpret_cast<const uint64_t*>(ws->h_scalars + 64);
   bool retry = false;
   for (int i = 0; i < comm_size(c); i++) retry = retry || (g[i] & SHARD_RETRY) != 0;
   bool again = false;
-  *rc = scan_overflowed(ws, &again);               // grows this rank's list when it was the one
+  *rc = scan_overflowed(a, ws, &again);            // grows this rank's list (or hands over to the walk kernel) when it was the one
   return !retry || *rc != AM_OK;
 }
 
@@ -733,10 +750,10 @@ int am_count_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_tex
   unsigned long long* ds = reinterpret_cast<unsigned long long*>(ws->d_scalars);
   for (int round = 0; !rc; round++) {
     rc = launch_scan(im, ws, *shard, MODE_COUNT, st);
-    if (!rc && launch_shard_total(ds, 0, 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc && launch_shard_total(ds, 0, 1, ds + 6, ws->last_kernel == 2 && !ws->last_inline ? ws->surv_bytes / 16 / std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) * std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
     if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);       // this rank's count -> every rank's
     if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
-    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (rc || shard_round_done(im, c, ws, &rc)) break;
     if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
   }
   if (!rc) comm_offsets(c, reinterpret_cast<const uint64_t*>(ws->h_scalars + 64), out);
@@ -754,10 +771,10 @@ int am_contains_any_sharded(const am_automaton* a, int cs, am_comm* c, const am_
   unsigned long long* ds = reinterpret_cast<unsigned long long*>(ws->d_scalars);
   for (int round = 0; !rc; round++) {
     rc = launch_scan(im, ws, *shard, MODE_ANY, st);                                        // d_scalars[8..16): this shard's flag (0 / 1)
-    if (!rc && launch_shard_total(ds, 1, 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc && launch_shard_total(ds, 1, 1, ds + 6, ws->last_kernel == 2 && !ws->last_inline ? ws->surv_bytes / 16 / std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) * std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
     if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
     if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
-    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (rc || shard_round_done(im, c, ws, &rc)) break;
     if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
   }
   if (!rc) {
@@ -783,10 +800,10 @@ int am_find_all_sharded(const am_automaton* a, int cs, am_comm* c, const am_dev_
   // path the ordering takes afterwards, so the all-gather goes on the stream right behind them and the host waits ONCE
   for (int round = 0; !rc; round++) {
     rc = emit_enqueue(im, ws, *shard, st, dev_out, dev_out ? cap : 0);
-    if (!rc && launch_shard_total(ds, 0, ws->emit_segmented ? 2 : 1, ds + 6, ws->surv ? ws->surv_bytes / 16 : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
+    if (!rc && launch_shard_total(ds, 0, ws->emit_segmented ? 2 : 1, ds + 6, ws->last_kernel == 2 && !ws->last_inline ? ws->surv_bytes / 16 / std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) * std::min<uint32_t>((uint32_t)sm_count(), SURV_REGIONS_MAX) : 0, ds + 4, st) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "count kernel");
     if (!rc) rc = comm_allgather_u64(c, ws->d_scalars + 32, ws->d_scalars + 64, st);
     if (!rc) rc = read_scalars(ws, st, 64 + 8 * (size_t)comm_size(c));
-    if (rc || shard_round_done(c, ws, &rc)) break;
+    if (rc || shard_round_done(im, c, ws, &rc)) break;
     if (round >= 3) rc = fail(AM_E_INTERNAL, "survivor count kept growing");
   }
   if (!rc) {

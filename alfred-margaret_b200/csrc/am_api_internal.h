@@ -30,12 +30,14 @@ struct Workspace {
   uint64_t* seg_bases = nullptr; size_t seg_bases_bytes = 0;
   uint32_t* seen_bits = nullptr; size_t seen_bytes = 0;        // containsAll: bit per needle rank
   ulonglong2* surv = nullptr; size_t surv_bytes = 0;           // filter scan: the survivor list {text index, 8 text bytes} between filter_kernel and verify_kernel
+  unsigned long long* surv_counts = nullptr;                   // ... and its per-CTA counters (SURV_REGIONS_MAX)
   cudaStream_t copy_stream = nullptr, scan_stream = nullptr;   // host-buffer scans: upload chunk k + 1 while chunk k is scanned
   cudaEvent_t copy_done[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;                    // profiling: around the scan kernel(s) of the last launch_scan
   bool emit_segmented = false; uint64_t num_segs = 0; uint32_t seg_cap = 0; uint64_t ovf_base = 0, ovf_cap = 0;
   int last_kernel = 0;                                         // kernel the last launch_scan really ran: 1 = walk, 2 = filter
   uint64_t last_span = 0;                                      // bytes the last launch_scan reported on
+  bool last_inline = false;                                    // ... and whether the filter kernel verified its survivors itself (no list to outgrow)
   bool force_walk = false;                                     // the next launch_scan takes the walk kernel (hand-over after a survivor flood)
   ~Workspace();
   int need_keys(uint64_t n);

@@ -53,10 +53,15 @@ struct ScanArgs {
   // filter kernel, IgnoreCase: 1 = `text` is the ORIGINAL text (one pass: folded probe, survivors lowered on the fly);
   // 0 = `text` is a lowered copy
   uint32_t ic_one_pass;
-  // filter scan: the positions that pass both filter levels (text indices) are listed here and verified by verify_kernel;
-  // *surv_count may exceed surv_cap (the list then holds the first surv_cap: the host repeats the scan with a larger list)
-  ulonglong2* surv; unsigned long long* surv_count; uint64_t surv_cap;   // entry: {text index, the eight text bytes at it}
+  // filter scan, list form: the positions that pass both filter levels are listed here and verified by verify_kernel.  Every
+  // CTA of filter_kernel owns a region of surv_cap_cta entries and its own counter (148 atomics on ONE address per flush
+  // round serialise in L2); a counter may exceed the capacity (the region then holds the first surv_cap_cta entries).
+  // verify_kernel sums up: surv_count[0] = regions * max counter (the capacity a complete list would have needed; the host
+  // repeats the scan with a larger list when it exceeds regions * surv_cap_cta), surv_count[1] = survivors in total (the
+  // inline form adds its own there: the host's survivor-rate monitor).
+  ulonglong2* surv; unsigned long long* surv_counts; unsigned long long* surv_count; uint64_t surv_cap_cta; uint32_t surv_regions;   // entry: {text index, the eight text bytes at it}
   uint32_t any_mode;            // containsAny: the kernels poll *d_flag and stop early
+  uint32_t force_list;          // development (AM_FILTER_LIST=1): take the list form where the inline form would run
   int* d_flag;                  // ANY
   uint32_t debug;               // development only (AM_DEBUG_FLAGS): 1 = probes only, 2 = no deep verify
   uint32_t krow;                // bytes per filter row (4 * copies) as a run-time value: keeps the address an IMAD (FMA pipe)

@@ -1,10 +1,17 @@
-// am_filter.cu -- the q-gram filter scan kernel of libam_b200 (see am_kernels.cu for the file-level notes).  It only
-// FILTERS: the positions that pass its two levels are appended to a list in global memory and verified by verify_kernel
-// (am_verify.cu), so the kernel is the same for every scan mode.
+// am_filter_impl.cuh -- the q-gram filter scan kernel of libam_b200 (see am_kernels.cu for the file-level notes).
+// Two forms of one kernel (template parameter IMODE):
+//   * IMODE = -1, "list": the kernel only FILTERS; the positions that pass its two levels are appended to a list in global
+//     memory and verified by verify_kernel (am_verify.cu), one survivor per thread.  IgnoreCase automata (whose verification
+//     lowers code points: a lot of code) and the long q-grams of large needle sets take this form: the scan warps never
+//     wait on a verification, and the hot loop's instruction footprint stays small.
+//   * IMODE = a ScanMode, "inline": CaseSensitive automata with q <= 4 verify their survivors in the kernel, 32 at a time,
+//     while the text they sit in is still in L2 -- measured 7 % faster on C2 than listing + verifying after the scan.
+// Instantiated by am_filter_list.cu and am_filter_inline.cu (two translation units, compiled in parallel).
 #include <cstddef>
 
 #include "am_device.cuh"
 #include "am_kernels.h"
+#include "am_verify.cuh"
 
 // The CTA's dynamic shared memory under an unmangled name, so that the kernel can take its shared-space address
 // with a plain `mov` (a compile-time constant) instead of converting a generic pointer.
@@ -31,13 +38,13 @@ constexpr int FK_WARPS = FK_THREADS / 32;
 #define FK_NPAIRS 4
 #endif
 #ifndef FK_DRAIN_AT
-#define FK_DRAIN_AT 16
+#define FK_DRAIN_AT 32
 #endif
 constexpr int FK_PAIRS = FK_NPAIRS;              // pairs of 512-byte warp iterations per warp chunk
 constexpr int FK_CHUNK = FK_PAIRS * 1024;        // bytes per warp chunk
 constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
 constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
-constexpr int FK_SQ = 32;                        // survivor stage entries per warp (16 bytes each)
+constexpr int FK_SQ = 48;                        // survivor stage entries per warp (16 bytes each; 24 KiB in all: with 32 KiB the kernel loses 4 % -- the last KiBs of L1)
 constexpr int FK_CAND = 384;                     // candidate list entries per warp (global second level)
 constexpr uint64_t FK_SPAN = 1ull << 40;         // bytes per launch (one launch per scan in practice; survivors carry 64-bit offsets)
 // Build-time variants (A/B-tested on the GPU; the rejected ones -- warp-scan compaction of the candidates, bulk L2
@@ -55,8 +62,9 @@ struct FilterSmem {
     uint16_t cand[FK_WARPS][FK_CAND];            // ... or, when the second level lives in global memory (q > 4), the warps' candidate lists
   };
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
-  ulonglong2 sq[FK_WARPS][FK_SQ];                // 16 KiB: survivor stage {text index, the eight text bytes there}, flushed to the global list
+  ulonglong2 sq[FK_WARPS][FK_SQ];                // 24 KiB: survivor stage {text index, the eight text bytes there}
   uint32_t sq_n[FK_WARPS];
+  uint32_t surv_n[FK_WARPS];                     // inline form: survivors verified so far (the host's survivor-rate monitor reads their sum)
   unsigned long long red[FK_WARPS];
   alignas(8) unsigned long long mbar;
 };
@@ -64,25 +72,44 @@ static_assert(sizeof(uint16_t) * FK_WARPS * FK_CAND <= sizeof(uint32_t) * T2_WOR
 
 // Stage one survivor: virtual index v = a0 + text index, and the eight text bytes at that position (as they stand in the
 // text, not folded): the verification of most survivors ends within them and never touches the text again.  A full stage
-// appends directly.
-__device__ __forceinline__ void fk_push(FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t a0, uint64_t v, uint32_t b_lo, uint32_t b_hi) {
+// appends to the list directly (list form) or verifies in place (inline form).
+template <int IMODE, int QK>
+__device__ __forceinline__ void fk_push(const DevAutomaton& A, FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t a0, uint64_t v, uint32_t b_lo, uint32_t b_hi,
+                                        unsigned long long& local_count) {
   if (v < a0) return;                                        // (bytes of the first granule that precede the text)
   const ulonglong2 e = make_ulonglong2(v - a0, (unsigned long long)b_lo | ((unsigned long long)b_hi << 32));
   const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
   if (qi < FK_SQ) { sm->sq[warp][qi] = e; return; }
-  const unsigned long long o = atomicAdd(a.surv_count, 1ull);
-  if (o < a.surv_cap) a.surv[o] = e;
+  if (IMODE < 0) {
+    const unsigned long long o = atomicAdd(a.surv_counts + blockIdx.x, 1ull);
+    if (o < a.surv_cap_cta) a.surv[(uint64_t)blockIdx.x * a.surv_cap_cta + o] = e;
+  } else {
+    fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, e.x, QK == 0 ? b_lo & A.qmask : b_lo, local_count);
+  }
 }
-// Append the warp's staged survivors to the global list (warp converged on entry and exit): one atomic, coalesced stores.
-__device__ __forceinline__ void fk_flush(FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t lane, uint32_t min_fill) {
+// The warp's staged survivors (warp converged on entry and exit): appended to the global list with one atomic and coalesced
+// stores (list form), or verified, one per lane (inline form).
+template <int IMODE, int QK>
+__device__ __forceinline__ void fk_flush(const DevAutomaton& A, FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t lane, uint32_t min_fill,
+                                         unsigned long long& local_count) {
   __syncwarp();
   uint32_t n = sm->sq_n[warp];
   if (n > FK_SQ) n = FK_SQ;
   if (n < min_fill || n == 0) return;
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(a.surv_count, (unsigned long long)n);
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
-  if (lane < n && base + lane < a.surv_cap) a.surv[base + lane] = sm->sq[warp][lane];
+  if (IMODE < 0) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.surv_counts + blockIdx.x, (unsigned long long)n);   // this CTA's own counter
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    ulonglong2* region = a.surv + (uint64_t)blockIdx.x * a.surv_cap_cta;
+    for (uint32_t k = lane; k < n; k += 32)
+      if (base + k < a.surv_cap_cta) region[base + k] = sm->sq[warp][k];
+  } else {
+    if (lane == 0) sm->surv_n[warp] += n;
+    for (uint32_t k = lane; k < n; k += 32) {
+      const ulonglong2 e = sm->sq[warp][k];
+      fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, e.x, QK == 0 ? (uint32_t)e.y & A.qmask : (uint32_t)e.y, local_count);
+    }
+  }
   __syncwarp();
   if (lane == 0) sm->sq_n[warp] = 0;
   __syncwarp();
@@ -225,7 +252,7 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
 // window and loads ONE word of the L2-resident bitmap -- all lanes busy, 64 independent loads in flight per warp --
 // instead of every lane popping its own candidates while the others wait.  Survivors (true q-gram hits + ~0.4 %) go to
 // the stage.  `m`: the lanes' candidate masks; cand_s: the warp's list (shared-space address).
-template <int QK, bool FOLD>
+template <int QK, bool FOLD, int IMODE>
 __device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint32_t m, uint32_t win_s, uint32_t cand_s, uint32_t lane,
                                                  uint32_t warp, uint32_t a0, uint64_t pair_v0, unsigned long long& local_count) {
   // ---- compaction: lane l writes its candidates' window offsets at [base_l, base_l + popc(m_l)) ----
@@ -273,7 +300,7 @@ __device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const Sc
 #if FK_DEBUG
         if (a.debug & 2u) { local_count++; continue; }
 #endif
-        fk_push(sm, a, warp, a0, pair_v0 + o[u], glo[u], ghi[u]);
+        fk_push<IMODE, QK>(A, sm, a, warp, a0, pair_v0 + o[u], glo[u], ghi[u], local_count);
       }
     }
     __syncwarp();
@@ -284,7 +311,7 @@ __device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const Sc
 // T2M:  second level: 0 = bitmaps in shared memory, 1 = exact keys in shared memory, 2 = bitmap in global memory (QK > 4).
 // FOLD: IgnoreCase automata (on a lowered copy of the text or, in one pass, on the original text: verify_kernel lowers the
 //       survivors on the fly): probe and second level see FOLDED bytes (every byte | 0x20).
-template <int QK, int T2M, bool FOLD>
+template <int QK, int T2M, bool FOLD, int IMODE>
 __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_constant__ DevAutomaton A, const __grid_constant__ ScanArgs a, uint64_t v_begin, uint64_t num_tiles) {
   FilterSmem* sm = reinterpret_cast<FilterSmem*>(am_fk_smem);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
                    "l"(reinterpret_cast<const unsigned char*>(A.filter2) + off), "r"(CH), "r"(smem_u32(&sm->mbar))
                    : "memory");
   }
-  if (lane == 0) sm->sq_n[warp] = 0;
+  if (lane == 0) { sm->sq_n[warp] = 0; sm->surv_n[warp] = 0; }
   __syncthreads();
   {
     uint32_t done = 0;
@@ -400,11 +427,11 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
         if (total <= FK_CAND) {
-          fk_global_rounds<QK, FOLD>(A, a, sm, m, win_s, cand_s, lane, warp, a0, rel0, local_count);
+          fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, m, win_s, cand_s, lane, warp, a0, rel0, local_count);
         } else {                                           // more than the list holds: a quarter of the positions at a time (<= 256 each)
 #pragma unroll 1
           for (uint32_t part = 0; part < 4; part++)
-            fk_global_rounds<QK, FOLD>(A, a, sm, m & (0xFFu << (8 * part)), win_s, cand_s, lane, warp, a0, rel0, local_count);
+            fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, m & (0xFFu << (8 * part)), win_s, cand_s, lane, warp, a0, rel0, local_count);
         }
       }
     } else {
@@ -420,13 +447,16 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
           if (a.debug & 2u) { local_count++; continue; }
 #endif
           // the four bytes after them (survivors only: two more window words)
-          const uint32_t wb = win_lane + (o & ~3u) + 4u;
-          const uint32_t raw_hi = __funnelshift_r(lds32(wb), lds32(wb + 4u), (o & 3u) * 8u);
-          fk_push(sm, a, warp, a0, v_begin + tile_rel + (pair_rel + o + (lane << 4)), g, raw_hi);
+          uint32_t raw_hi = 0;                                 // (the inline form verifies from the q-gram alone)
+          if (IMODE < 0) {
+            const uint32_t wb = win_lane + (o & ~3u) + 4u;
+            raw_hi = __funnelshift_r(lds32(wb), lds32(wb + 4u), (o & 3u) * 8u);
+          }
+          fk_push<IMODE, QK>(A, sm, a, warp, a0, v_begin + tile_rel + (pair_rel + o + (lane << 4)), g, raw_hi, local_count);
         }
       }
     }
-    fk_flush(sm, a, warp, lane, FK_DRAIN_AT);              // only when a full round of survivors waits
+    fk_flush<IMODE, QK>(A, sm, a, warp, lane, FK_DRAIN_AT, local_count);   // only when a full round of survivors waits
   };
 
   static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
@@ -436,7 +466,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   uint2 tC, tN;
   if (blockIdx.x < num_tiles) load_pair(g_next, cA, cB, tC);
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    if (a.any_mode && *reinterpret_cast<volatile int*>(a.d_flag)) break;   // containsAny: an earlier launch's verification found a match
+    if (a.any_mode && *reinterpret_cast<volatile int*>(a.d_flag)) break;   // containsAny: a match has been found (inline form: by another CTA)
     const uint64_t tile_rel = tile * FK_TILE;              // this tile, relative to v_begin
     const uint32_t chunk_rel = warp * FK_CHUNK;            // this warp's chunk, relative to the tile
 #pragma unroll 1
@@ -449,10 +479,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       process_pair(nA, nB, tN, tile_rel, chunk_rel + (uint32_t)pair * 1024u + 1024u);
     }
   }
-  fk_flush(sm, a, warp, lane, 1);
+  fk_flush<IMODE, QK>(A, sm, a, warp, lane, 1, local_count);
+  if (IMODE >= 0 && lane == 0 && sm->surv_n[warp]) atomicAdd(a.surv_count + 1, (unsigned long long)sm->surv_n[warp]);
 
-#if FK_DEBUG
-  if (a.debug) {                                             // stage-isolation counters land in d_count
+  if (IMODE == MODE_COUNT || (FK_DEBUG && a.debug)) {        // (the stage-isolation counters of FK_DEBUG builds land in d_count too)
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
     if (lane == 0) sm->red[warp] = local_count;
     __syncthreads();
@@ -462,14 +492,13 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       if (s) atomicAdd(a.d_count, s);
     }
   }
-#endif
 }
 
-template <int QK, int T2M, bool FOLD>
+template <int QK, int T2M, bool FOLD, int IMODE>
 static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
   static std::atomic<uint64_t> attr_done{0};   // per device (am_options.device: one process may use several GPUs)
   {
-    cudaError_t e = ensure_dynamic_smem(filter_kernel<QK, T2M, FOLD>, (int)sizeof(FilterSmem), attr_done);
+    cudaError_t e = ensure_dynamic_smem(filter_kernel<QK, T2M, FOLD, IMODE>, (int)sizeof(FilterSmem), attr_done);
     if (e != cudaSuccess) return e;
   }
   const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
@@ -481,33 +510,11 @@ static cudaError_t launch_filter_t(const DevAutomaton& A, const ScanArgs& a, cud
     const uint64_t tiles = (span + FK_TILE - 1) / FK_TILE;
     const uint64_t blocks = tiles < (uint64_t)sm_count() ? tiles : (uint64_t)sm_count();
     g_kernel_launches++;
-    filter_kernel<QK, T2M, FOLD><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
+    filter_kernel<QK, T2M, FOLD, IMODE><<<(unsigned)blocks, FK_THREADS, sizeof(FilterSmem), st>>>(A, a, v0, tiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
-
-template <bool FOLD>
-static cudaError_t launch_filter_c(const DevAutomaton& A, const ScanArgs& a, cudaStream_t st) {
-  const bool x = A.t2_exact != 0;
-  switch (A.q) {
-    case 8: return x ? cudaErrorInvalidValue : launch_filter_t<8, 2, FOLD>(A, a, st);
-    case 6: return x ? cudaErrorInvalidValue : launch_filter_t<6, 2, FOLD>(A, a, st);
-    case 4: return x ? launch_filter_t<4, 1, FOLD>(A, a, st) : launch_filter_t<4, 0, FOLD>(A, a, st);
-    case 1: case 2: case 3: return x ? launch_filter_t<0, 1, FOLD>(A, a, st) : launch_filter_t<0, 0, FOLD>(A, a, st);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-// The filter scan: filter_kernel lists the survivors, verify_kernel (am_verify.cu) turns them into matches.
-cudaError_t launch_filter(const DevAutomaton& A, const ScanArgs& a, int mode, cudaStream_t st) {
-  if (a.text_len <= a.report_begin) return cudaSuccess;
-  cudaError_t e = A.ignore_case ? launch_filter_c<true>(A, a, st) : launch_filter_c<false>(A, a, st);
-  if (e != cudaSuccess) return e;
-  return launch_verify(A, a, mode, st);
-}
-
-int filter_kernel_smem_bytes() { return (int)sizeof(FilterSmem); }
 
 }  // namespace am

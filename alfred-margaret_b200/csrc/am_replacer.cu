@@ -33,6 +33,7 @@ struct am_replacer {
   uint8_t* d_repl = nullptr;
   void* d_idinfo[2] = {nullptr, nullptr};  // per case mode: IdInfo of every needle id (rank in that image, replacement, payload lengths)
   std::mutex mu;
+  std::vector<void*> scratch_pool;         // idle ReplacerScratch sets (one per concurrent run)
   bool has_empty = false;
   bool stored_len_differs = false;       // some stored (lowered) needle has another byte length than the original
 };
@@ -51,6 +52,12 @@ struct DevBuf {
   }
   ~DevBuf() { if (p) cudaFree(p); }
   template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+// Device scratch of one Replacer run, kept with the replacer between runs (a run on a 2 GiB text holds ~7 GiB of tiles, lists
+// and buffers: allocating and freeing them per call costs more than the passes).
+struct ReplacerScratch {
+  DevBuf contig, tiles, tile_len, tile_base[2], tile_flag, touched, new_len, sel, starts, ends, keep, kidx, kstart, kend, kdelta, kshift, cubtmp, scal, spare, keys_c, rkeys;
 };
 
 struct RankIs {
@@ -849,12 +856,27 @@ static int replacer_core_tiled(const am_replacer* r, const Image* a, int cs, con
                                uint8_t** d_out, uint64_t* out_len, int* exceeded) {
   *d_out = nullptr; *out_len = 0; *exceeded = 0; g_last_passes = 0; g_last_rescans = 0; g_last_replacer_ms = 0.f; g_last_replacer_bytes = 0;
   Workspace* ws = acquire_ws(a); if (!ws) return fail(AM_E_OOM, "workspace");
-  DevBuf contig, tiles, tile_len, tile_base[2], tile_flag, touched, new_len, sel, starts, ends, keep, kidx, kstart, kend, kdelta, kshift, cubtmp, scal;
+  ReplacerScratch* box = nullptr;
+  {
+    am_replacer* mr = const_cast<am_replacer*>(r);
+    std::lock_guard<std::mutex> g(mr->mu);
+    if (!mr->scratch_pool.empty()) { box = static_cast<ReplacerScratch*>(mr->scratch_pool.back()); mr->scratch_pool.pop_back(); }
+  }
+  if (!box) box = new ReplacerScratch();
+  ReplacerScratch& S = *box;
+  DevBuf &contig = S.contig, &tiles = S.tiles, &tile_len = S.tile_len, (&tile_base)[2] = S.tile_base, &tile_flag = S.tile_flag, &touched = S.touched, &new_len = S.new_len,
+         &sel = S.sel, &starts = S.starts, &ends = S.ends, &keep = S.keep, &kidx = S.kidx, &kstart = S.kstart, &kend = S.kend, &kdelta = S.kdelta, &kshift = S.kshift,
+         &cubtmp = S.cubtmp, &scal = S.scal, &spare = S.spare, &keys_c = S.keys_c, &rkeys = S.rkeys;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   const bool prof = profiling_enabled();
   int rc;
   auto done = [&](int code) {
     if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+    {
+      am_replacer* mr = const_cast<am_replacer*>(r);
+      std::lock_guard<std::mutex> g(mr->mu);
+      mr->scratch_pool.push_back(box);
+    }
     release_ws(a, ws); return code;
   };
   const IdInfo* d_info = nullptr;
@@ -908,8 +930,8 @@ static int replacer_core_tiled(const am_replacer* r, const Image* a, int cs, con
 
   bool have_list = false;
   uint64_t n = 0;
-  DevBuf spare;                                    // second contiguous buffer of the overflow path
-  DevBuf keys_c, rkeys;                            // the match list ping-pongs between ws->keys_b and keys_c; rkeys: rescanned matches of a pass
+  // (S.spare: second contiguous buffer of the overflow path; the match list ping-pongs between ws->keys_b and S.keys_c; S.rkeys:
+  // the rescanned matches of a pass)
   uint64_t* list = nullptr;                        // the current (sorted) match list
   uint64_t* other = nullptr;
   for (;;) {
@@ -1160,6 +1182,7 @@ void am_replacer_free(am_replacer* r) {
     if (r->automaton && r->automaton->device >= 0) g.enter(r->automaton->device);
     cudaFree(r->d_repl);
     for (void* p : r->d_idinfo) if (p) cudaFree(p);
+    for (void* b : r->scratch_pool) delete static_cast<ReplacerScratch*>(b);
   }
   if (r->automaton) am_automaton_free(r->automaton);
   delete r;

@@ -1,8 +1,17 @@
 """Summarise an .ncu-rep (development aid): key metrics, stall mix, hottest SASS regions."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
+want = None
+if "--kernel" in sys.argv:                       # pick the first launch whose name holds this substring (default: the first launch)
+    k = sys.argv.index("--kernel"); want = sys.argv[k + 1]; del sys.argv[k:k + 2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw))); hdr, units, vals = rows[0], rows[1], rows[2]
+rows = [r for r in csv.reader(io.StringIO(raw)) if r]
+if len(rows) < 3:
+    print("no kernel launches in", rep); sys.exit(0)
+hdr, units = rows[0], rows[1]
+iname = hdr.index('Kernel Name') if 'Kernel Name' in hdr else None
+vals = next((r for r in rows[2:] if want is None or (iname is not None and want in r[iname])), rows[2])
+if iname is not None: print("kernel:", vals[iname][:110])
 keys = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','launch__registers_per_thread','smsp__inst_executed.sum',
  'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
  'smsp__issue_active.avg.pct_of_peak_sustained_active','smsp__thread_inst_executed_per_inst_executed.ratio','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
@@ -17,7 +26,10 @@ for i, h in enumerate(hdr):
 tot = sum(v for v, _ in st) or 1
 print("stalls: " + "  ".join("%s %.1f%%" % (h, 100 * v / tot) for v, h in sorted(st, reverse=True)[:9]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; data = rows[2:]
+rows = [r for r in csv.reader(io.StringIO(src)) if r]
+if len(rows) < 3 or 'Source' not in rows[1]:
+    print("(no source page)"); sys.exit(0)
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 isrc, ins, ith, isam = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Avg. Threads Executed'), hdr.index('# Samples')
 tot = sum(int(r[ins]) for r in data); tots = sum(int(r[isam]) for r in data) or 1
 regions, cur = [], None

@@ -637,3 +637,36 @@ def test_ignore_case_one_pass_any_text(am, oracle, lower_dense, torch_cuda):
             got = mm.find_all(hb)
             assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), (count, lo_len, force)
             assert mm.count_matches(hb) == len(want)
+
+
+def test_survivor_flood_hands_over_to_the_walk(am, oracle, torch_cuda):
+    """Texts that defeat the q-gram filter -- "aaaa..." against needles of a's, a periodic text made of the needles' own
+    q-grams: (nearly) every position survives both filter levels.  The survivor-rate monitor hands such a scan over to the
+    per-segment walk (O(n) on any input, like the reference's loop, Automaton.hs:489-510); the results must not change, in
+    any mode, also when only PART of a host text (one 64 MiB chunk of several) floods."""
+    from alfred_margaret_b200 import synth
+    n = (3 << 20) + 5
+    cases = [([b"aaaa", b"aaaaaa", b"aaab", b"baaa"], np.full(n, ord("a"), dtype=np.uint8)),
+             ([b"abcabc", b"bcabca", b"cabcab", b"abcabcabc"], np.frombuffer((b"abc" * (n // 3 + 1))[:n], dtype=np.uint8).copy())]
+    for needles, hay in cases:
+        hay[n // 2] = ord("b")
+        want = oracle.Machine(needles).find_all(hay, threads=4, cap=4 * n)
+        assert len(want) > n
+        m = machine(am, needles)
+        assert m.info()["kernel_kind"] == 2
+        for _ in range(3):                                     # (the third scan starts on the walk kernel: two hand-overs in a row)
+            got = m.find_all(hay)
+            assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])
+        assert m.count_matches(hay) == len(want) and m.contains_any(hay) is True
+        dev = torch_cuda.from_numpy(hay).cuda()
+        assert m.count_matches_dev(dev.data_ptr(), n) == len(want)
+    # ordinary text before and after a flooded stretch: the filter comes back (every eighth scan tries it again)
+    needles = synth.random_needles(500, 42) + [b"aaaa"]
+    hay = synth.fill_host(0, 2 << 20, 43)
+    synth.plant_host(hay, 0, 44, needles)
+    hay[(1 << 20):(1 << 20) + 300000] = ord("a")
+    want = oracle.Machine(needles).find_all(hay, threads=4, cap=1 << 22)
+    m = machine(am, needles)
+    for _ in range(10):
+        got = m.find_all(hay)
+        assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"])

@@ -196,3 +196,21 @@ def test_incremental_passes_equal_full_rescans(am, oracle, monkeypatch):
     r = R.build(0, pairs)
     assert R.run_with_limit(r, len(full) + 4096, hay) == oracle.Replacer(pairs).run_with_limit(hay, len(full) + 4096)
     assert R.run_with_limit(r, 10, hay) is None and oracle.Replacer(pairs).run_with_limit(hay, 10) is None
+
+
+def test_periodic_text_is_one_overlap_cluster(am, oracle):
+    """removeOverlap (Replacer.hs:191-198) on a text where every match overlaps its predecessor: "aa" in a long run of a's is
+    ONE cluster of a million matches; the kept ones are every second.  (The cluster walk is warp-cooperative; a serial walk
+    of this list took seconds.)  Also a needle that overlaps itself at distance 2 and deletions that join."""
+    R = am.replacer
+    n = (1 << 20) + 3
+    for pairs, text in (([("aa", "b")], b"a" * n), ([("aba", "X"), ("bX", "")], b"ab" * (n // 2) + b"a"), ([("aa", ""), ("ba", "c")], b"baaa" * (n // 4))):
+        want = oracle.Replacer(pairs, cs=0).run(text)
+        r = R.build(0, pairs)
+        assert R.run(r, text) == want
+        import os
+        os.environ["AM_REPLACER_RESCAN"] = "1"
+        try:
+            assert R.run(r, text) == want                              # the literal pass structure agrees
+        finally:
+            del os.environ["AM_REPLACER_RESCAN"]
