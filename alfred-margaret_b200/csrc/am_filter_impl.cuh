@@ -76,43 +76,49 @@ static_assert(sizeof(uint16_t) * FK_WARPS * FK_CAND <= sizeof(uint32_t) * T2_WOR
 template <int IMODE, int QK>
 __device__ __forceinline__ void fk_push(const DevAutomaton& A, FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t a0, uint64_t v, uint32_t b_lo, uint32_t b_hi,
                                         unsigned long long& local_count) {
-  if (v < a0) return;                                        // (bytes of the first granule that precede the text)
-  const ulonglong2 e = make_ulonglong2(v - a0, (unsigned long long)b_lo | ((unsigned long long)b_hi << 32));
+  // (one structured if / else and no early return: ptxas then proves that the warp reconverges after the candidate loop.
+  // With early returns here it did not -- a plain BSSY instead of BSSY.RECONVERGENT -- and 18 % of the pairs went on in
+  // pieces: +9 % instructions, the flush check and the next pair's shuffles on their slow paths)
+  const ulonglong2 e = make_ulonglong2(v, (unsigned long long)b_lo | ((unsigned long long)b_hi << 32));   // v < a0: bytes of the first granule that precede the text (dropped at the flush)
   const uint32_t qi = atomicAdd(&sm->sq_n[warp], 1u);
-  if (qi < FK_SQ) { sm->sq[warp][qi] = e; return; }
-  if (IMODE < 0) {
-    const unsigned long long o = atomicAdd(a.surv_counts + blockIdx.x, 1ull);
-    if (o < a.surv_cap_cta) a.surv[(uint64_t)blockIdx.x * a.surv_cap_cta + o] = e;
-  } else {
-    fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, e.x, QK == 0 ? b_lo & A.qmask : b_lo, local_count);
+  if (qi < FK_SQ) {
+    sm->sq[warp][qi] = e;
+  } else if (v >= a0) {
+    if (IMODE < 0) {
+      const unsigned long long o = atomicAdd(a.surv_counts + blockIdx.x, 1ull);
+      if (o < a.surv_cap_cta) a.surv[(uint64_t)blockIdx.x * a.surv_cap_cta + o] = e;
+    } else {
+      fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, v - a0, QK == 0 ? b_lo & A.qmask : b_lo, local_count);
+    }
   }
 }
 // The warp's staged survivors (warp converged on entry and exit): appended to the global list with one atomic and coalesced
 // stores (list form), or verified, one per lane (inline form).
 template <int IMODE, int QK>
-__device__ __forceinline__ void fk_flush(const DevAutomaton& A, FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t lane, uint32_t min_fill,
+__device__ __forceinline__ void fk_flush(const DevAutomaton& A, FilterSmem* sm, const ScanArgs& a, uint32_t warp, uint32_t lane, uint32_t a0, uint32_t min_fill,
                                          unsigned long long& local_count) {
   __syncwarp();
   uint32_t n = sm->sq_n[warp];
   if (n > FK_SQ) n = FK_SQ;
-  if (n < min_fill || n == 0) return;
-  if (IMODE < 0) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(a.surv_counts + blockIdx.x, (unsigned long long)n);   // this CTA's own counter
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    ulonglong2* region = a.surv + (uint64_t)blockIdx.x * a.surv_cap_cta;
-    for (uint32_t k = lane; k < n; k += 32)
-      if (base + k < a.surv_cap_cta) region[base + k] = sm->sq[warp][k];
-  } else {
-    if (lane == 0) sm->surv_n[warp] += n;
-    for (uint32_t k = lane; k < n; k += 32) {
-      const ulonglong2 e = sm->sq[warp][k];
-      fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, e.x, QK == 0 ? (uint32_t)e.y & A.qmask : (uint32_t)e.y, local_count);
+  if (n >= min_fill && n != 0) {
+    if (IMODE < 0) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.surv_counts + blockIdx.x, (unsigned long long)n);   // this CTA's own counter
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      ulonglong2* region = a.surv + (uint64_t)blockIdx.x * a.surv_cap_cta;
+      for (uint32_t k = lane; k < n; k += 32)
+        if (base + k < a.surv_cap_cta) region[base + k] = sm->sq[warp][k];   // (virtual indices: verify_kernel drops v < a0 and subtracts a0)
+    } else {
+      if (lane == 0) sm->surv_n[warp] += n;
+      for (uint32_t k = lane; k < n; k += 32) {
+        const ulonglong2 e = sm->sq[warp][k];
+        if (e.x >= a0) fk_verify_short<IMODE < 0 ? 0 : IMODE>(A, a, e.x - a0, QK == 0 ? (uint32_t)e.y & A.qmask : (uint32_t)e.y, local_count);
+      }
     }
+    __syncwarp();
+    if (lane == 0) sm->sq_n[warp] = 0;
+    __syncwarp();
   }
-  __syncwarp();
-  if (lane == 0) sm->sq_n[warp] = 0;
-  __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   constexpr bool S2 = QK == 4;
   constexpr int COPIES = QK > 4 ? 1 : S2 ? filter_copies_s2(T2M == 1) : FK_COPIES_S1;
   static_assert(T2M != 2 || QK > 4, "the global second level serves the long q-grams");
+  constexpr bool TAIL8 = QK > 4 || IMODE < 0;                // the window carries two words beyond the pair (long q-grams; the list form's eight text bytes per survivor)
 
   // ---- stage the filter bitmap and T2 into shared memory with TMA bulk copies -----------------------
   if (threadIdx.x == 0) {
@@ -370,14 +377,16 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       const uint4* p = base16 + g + lane;
       qa = ld_stream_v4(p);
       qb = ld_stream_v4(p + 32);
-      tail = __ldg(reinterpret_cast<const uint2*>(base16 + g + 64));
+      if (TAIL8) tail = __ldg(reinterpret_cast<const uint2*>(base16 + g + 64));
+      else tail = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(base16 + g + 64)), 0u);   // (the inline form looks one word ahead)
     } else {
       const uint64_t last = nvec - 1;
       const uint64_t ga = g + lane < last ? g + lane : last, gb = g + lane + 32 < last ? g + lane + 32 : last;
       const uint64_t gt = g + 64 < last ? g + 64 : last;
       qa = ld_stream_v4(base16 + ga);
       qb = ld_stream_v4(base16 + gb);
-      tail = __ldg(reinterpret_cast<const uint2*>(base16 + gt));
+      if (TAIL8) tail = __ldg(reinterpret_cast<const uint2*>(base16 + gt));
+      else tail = make_uint2(__ldg(reinterpret_cast<const uint32_t*>(base16 + gt)), 0u);
     }
   };
   auto process_pair = [&](const uint4& qa_in, const uint4& qb_in, const uint2& tail_in, uint64_t tile_rel, uint32_t pair_rel) {
@@ -386,7 +395,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
     // mirror the pair into the window (q-gram recovery for the few candidates)
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane), "r"(qa.x), "r"(qa.y), "r"(qa.z), "r"(qa.w) : "memory");
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(win_lane + 512u), "r"(qb.x), "r"(qb.y), "r"(qb.z), "r"(qb.w) : "memory");
-    if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(win_s + 1024u), "r"(tail.x), "r"(tail.y) : "memory");
+    if (lane == 0) {
+      if (TAIL8) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(win_s + 1024u), "r"(tail.x), "r"(tail.y) : "memory");
+      else asm volatile("st.shared.u32 [%0], %1;" ::"r"(win_s + 1024u), "r"(tail.x) : "memory");
+    }
     if (FOLD) {
       // IgnoreCase automata hold the cells of FOLDED q-grams: one OR per word here.  The text itself stays in the window.
       qa.x |= FOLD_MASK; qa.y |= FOLD_MASK; qa.z |= FOLD_MASK; qa.w |= FOLD_MASK;
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
         }
       }
     }
-    fk_flush<IMODE, QK>(A, sm, a, warp, lane, FK_DRAIN_AT, local_count);   // only when a full round of survivors waits
+    fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, FK_DRAIN_AT, local_count);   // only when a full round of survivors waits
   };
 
   static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
@@ -466,7 +478,18 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   uint2 tC, tN;
   if (blockIdx.x < num_tiles) load_pair(g_next, cA, cB, tC);
   for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    if (a.any_mode && *reinterpret_cast<volatile int*>(a.d_flag)) break;   // containsAny: a match has been found (inline form: by another CTA)
+    // containsAny: stop once a match has been flagged.  Inline form: by any CTA of this launch, hence a volatile poll -- compiled
+    // into the ANY kernels only: around a STRONG load that decides a loop exit ptxas assumes a spin loop, plants YIELD and drops
+    // the reconvergence guarantee of the loops inside (measured on C2: 18 % of the pairs then ran in pieces, +9 % instructions,
+    // -10 % throughput -- in every mode, when the poll was a run-time switch).  List form: only verify_kernel sets the flag, i.e.
+    // an EARLIER launch (a previous chunk of the text); a weak load is enough for that and keeps the loops reconvergent.
+    if (IMODE == MODE_ANY) {
+      if (*reinterpret_cast<volatile int*>(a.d_flag)) break;
+    } else if (IMODE < 0 && a.any_mode) {
+      int f;
+      asm volatile("ld.global.s32 %0, [%1];" : "=r"(f) : "l"(a.d_flag) : "memory");
+      if (f) break;
+    }
     const uint64_t tile_rel = tile * FK_TILE;              // this tile, relative to v_begin
     const uint32_t chunk_rel = warp * FK_CHUNK;            // this warp's chunk, relative to the tile
 #pragma unroll 1
@@ -479,7 +502,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       process_pair(nA, nB, tN, tile_rel, chunk_rel + (uint32_t)pair * 1024u + 1024u);
     }
   }
-  fk_flush<IMODE, QK>(A, sm, a, warp, lane, 1, local_count);
+  fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, 1, local_count);
   if (IMODE >= 0 && lane == 0 && sm->surv_n[warp]) atomicAdd(a.surv_count + 1, (unsigned long long)sm->surv_n[warp]);
 
   if (IMODE == MODE_COUNT || (FK_DEBUG && a.debug)) {        // (the stage-isolation counters of FK_DEBUG builds land in d_count too)

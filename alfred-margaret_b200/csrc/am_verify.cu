@@ -31,13 +31,15 @@ __global__ void __launch_bounds__(256) verify_kernel(const __grid_constant__ Dev
   }
   __syncthreads();
   const unsigned long long n = start[R];
+  const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
   unsigned long long local_count = 0;
   for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
     uint32_t lo = 0, hi = R;                                   // the region that holds survivor k
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (start[mid] <= k) lo = mid; else hi = mid; }
-    const ulonglong2 e = a.surv[(uint64_t)lo * a.surv_cap_cta + (k - start[lo])];
-    fk_deep_verify<MODE, LOWER>(A, a, e.x, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
+    const ulonglong2 e = a.surv[(uint64_t)lo * a.surv_cap_cta + (k - start[lo])];   // {virtual index = a0 + text index, eight text bytes}
+    if (e.x < a0) continue;                                    // bytes of the first granule that precede the text
+    fk_deep_verify<MODE, LOWER>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
   }
   if (MODE == MODE_COUNT) {
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);
