@@ -472,7 +472,16 @@ void host_filter_model(const HostAutomaton& H, const uint8_t* d, uint64_t n, uin
       const uint32_t b2 = filter2_bit(g);
       level2 = (H.filter2[b2 >> 5] >> (b2 & 31)) & 1u;
     }
-    out_flags[i] = (uint8_t)(level1 | (level2 << 1));
+    uint32_t level3 = 1;                                       // (images without a third level pass everything)
+    if (q == 4 && !exact && H.gbits_log2 != 0) {
+      level3 = 0;
+      const uint32_t hi = gram4(i + 4);
+      for (uint32_t L = 4; L <= 8; L++) {
+        const uint32_t b3 = gp_hash(g, L == 4 ? 0u : hi & (L == 8 ? 0xFFFFFFFFu : ((1u << (8 * (L - 4))) - 1u)), L) >> (32 - H.gbits_log2);
+        level3 |= (H.gbits[b3 >> 5] >> (b3 & 31)) & 1u;
+      }
+    }
+    out_flags[i] = (uint8_t)(level1 | (level2 << 1) | (level3 << 2));
   }
 }
 

@@ -539,6 +539,56 @@ int build_host_automaton(const am_u8slice* needles, size_t n, int cs, const am_l
         set_bit(T2B_WORD0, t2b_bit(g, x.next));
         set_bit(T2C_WORD0, t2c_bit(g, x.next));
       }
+      if (q == 4 && A->ic_fold_ok) {
+        // third level (global memory): the (folded) prefix of min(length, 8) bytes of every string the trie holds -- IgnoreCase: of
+        // every case variant of the code points that reach into it -- keyed with its length (gp_hash)
+        std::unordered_set<uint64_t> keys[9];
+        bool ok = true;
+        std::vector<uint8_t> buf;
+        for (const auto& str : inserted) {
+          const uint32_t L = (uint32_t)std::min<size_t>(str.size(), 8);
+          auto emit = [&](const uint8_t* b) {
+            uint64_t g = 0;
+            for (uint32_t k = 0; k < L; k++) g |= (uint64_t)b[k] << (8 * k);
+            if (ic) g = (g | 0x2020202020202020ull) & gram_mask(L);
+            keys[L].insert(g);
+          };
+          if (!ic) { emit(str.data()); continue; }
+          std::vector<std::vector<uint32_t>> opts;
+          uint32_t covered = 0;
+          size_t combos = 1;
+          while (covered < L) {
+            uint32_t c; covered += decode(str.data(), (uint32_t)str.size(), covered, &c);
+            std::vector<uint32_t> o{c};
+            auto it = same_pre.find(c);
+            if (c >= 128 && it != same_pre.end()) for (uint32_t f : it->second) if (utf8_len(f) == utf8_len(c)) o.push_back(f);
+            combos *= o.size();
+            opts.push_back(std::move(o));
+            if (combos > MAX_CASE_VARIANTS) break;
+          }
+          if (combos > MAX_CASE_VARIANTS) { ok = false; break; }   // (this image does without the third level)
+          std::vector<size_t> choice(opts.size(), 0);
+          for (size_t v = 0; v < combos; v++) {
+            buf.clear();
+            for (size_t p = 0; p < opts.size(); p++) encode(opts[p][choice[p]], &buf);
+            buf.resize(std::max<size_t>(buf.size(), 8), 0);
+            emit(buf.data());
+            for (size_t p = 0; p < opts.size(); p++) { if (++choice[p] < opts[p].size()) break; choice[p] = 0; }
+          }
+        }
+        if (ok) {
+          size_t nkeys = 0;
+          for (auto& k : keys) nkeys += k.size();
+          A->gbits_log2 = 20;
+          while (A->gbits_log2 < 27 && (1ull << A->gbits_log2) < (uint64_t)nkeys * 256) A->gbits_log2++;
+          A->gbits.assign((size_t)1 << (A->gbits_log2 - 5), 0);
+          for (uint32_t L = 4; L <= 8; L++)
+            for (uint64_t g : keys[L]) {
+              const uint32_t b = gp_hash((uint32_t)g, (uint32_t)(g >> 32), L) >> (32 - A->gbits_log2);
+              A->gbits[b >> 5] |= 1u << (b & 31);
+            }
+        }
+      }
     }
   }
   return AM_OK;

@@ -46,6 +46,7 @@ constexpr int FK_TILE = FK_WARPS * FK_CHUNK;     // bytes per CTA tile (128 KiB)
 constexpr int FK_WIN_WORDS = 256 + 4;            // window: 1 KiB pair + tail word (padded to 16 B)
 constexpr int FK_SQ = 48;                        // survivor stage entries per warp (16 bytes each; 24 KiB in all: with 32 KiB the kernel loses 4 % -- the last KiBs of L1)
 constexpr int FK_CAND = 384;                     // candidate list entries per warp (global second level)
+constexpr int FK_CAND0 = 128;                    // candidate list entries per warp (bitmap second level in shared memory: 4 positions x 32 lanes always fit)
 constexpr uint64_t FK_SPAN = 1ull << 40;         // bytes per launch (one launch per scan in practice; survivors carry 64-bit offsets)
 // Build-time variants (A/B-tested on the GPU; the rejected ones -- warp-scan compaction of the candidates, bulk L2
 // prefetch, IMAD.HI row addressing, an out-of-line survivor drain -- are recorded in profiles/README.md):
@@ -63,6 +64,7 @@ struct FilterSmem {
   };
   uint32_t window[FK_WARPS][FK_WIN_WORDS];       // 32.5 KiB
   ulonglong2 sq[FK_WARPS][FK_SQ];                // 24 KiB: survivor stage {text index, the eight text bytes there}
+  uint16_t cand0[FK_WARPS][FK_CAND0];            //  8 KiB: the warps' candidate lists when the second level is the bitmaps in `t2` (large needle sets, q <= 4)
   uint32_t sq_n[FK_WARPS];
   uint32_t surv_n[FK_WARPS];                     // inline form: survivors verified so far (the host's survivor-rate monitor reads their sum)
   unsigned long long red[FK_WARPS];
@@ -252,23 +254,18 @@ __device__ __forceinline__ bool fk_phase_a(const DevAutomaton& A, uint32_t win_s
   }
 }
 
-// Second level in GLOBAL memory (T2M = 2; q = 6, 8: needle sets of 10^4 .. 10^6 keys, whose level-1 bitmap passes several
-// per cent of the positions).  The candidates of the warp's pair are compacted into a list in shared memory (a warp
-// scan over the lanes' candidate counts) and looked up 32 at a time: every lane recovers one candidate's q-gram from the
-// window and loads ONE word of the L2-resident bitmap -- all lanes busy, 64 independent loads in flight per warp --
-// instead of every lane popping its own candidates while the others wait.  Survivors (true q-gram hits + ~0.4 %) go to
-// the stage.  `m`: the lanes' candidate masks; cand_s: the warp's list (shared-space address).
-template <int QK, bool FOLD, int IMODE>
-__device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint32_t m, uint32_t win_s, uint32_t cand_s, uint32_t lane,
-                                                 uint32_t warp, uint32_t a0, uint64_t pair_v0, unsigned long long& local_count) {
-  // ---- compaction: lane l writes its candidates' window offsets at [base_l, base_l + popc(m_l)) ----
-  const uint32_t cnt = __popc(m);
-  uint32_t incl = cnt;
+// Compaction of the warp's candidates (bit P of a lane's m = position P of its 32).  fk_scan: inclusive prefix sum of the lanes'
+// candidate counts, returns the warp's total.  fk_scatter: lane l writes the window offsets of its candidates at
+// [incl_l - popc(m_l), incl_l) of the warp's list in shared memory.
+__device__ __forceinline__ uint32_t fk_scan(uint32_t m, uint32_t lane, uint32_t* incl_out) {
+  uint32_t incl = __popc(m);
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (uint32_t)d) incl += t; }
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  if (total == 0) return;
-  uint32_t at = cand_s + ((incl - cnt) << 1);
+  *incl_out = incl;
+  return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+__device__ __forceinline__ void fk_scatter(uint32_t m, uint32_t incl, uint32_t cand_s, uint32_t lane) {
+  uint32_t at = cand_s + ((incl - __popc(m)) << 1);
   while (m) {
     uint32_t P;
     asm("bfind.u32 %0, %1;" : "=r"(P) : "r"(m));
@@ -278,6 +275,19 @@ __device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const Sc
     at += 2;
   }
   __syncwarp();
+}
+
+// Second level in GLOBAL memory (T2M = 2; q = 6, 8: needle sets of 10^4 .. 10^6 keys, whose level-1 bitmap passes several
+// per cent of the positions).  The candidates of the warp's pair are compacted into a list in shared memory (a warp
+// scan over the lanes' candidate counts) and looked up 32 at a time: every lane recovers one candidate's q-gram from the
+// window and loads ONE word of the L2-resident bitmap -- all lanes busy, 64 independent loads in flight per warp --
+// instead of every lane popping its own candidates while the others wait.  Survivors (true q-gram hits + ~0.4 %) go to
+// the stage.  `m`: the lanes' candidate masks; cand_s: the warp's list (shared-space address).
+template <int QK, bool FOLD, int IMODE>
+__device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint32_t m, uint32_t incl, uint32_t total, uint32_t win_s,
+                                                 uint32_t cand_s, uint32_t lane, uint32_t warp, uint32_t a0, uint64_t pair_v0, unsigned long long& local_count) {
+  if (total == 0) return;
+  fk_scatter(m, incl, cand_s, lane);
   // ---- rounds of 64 candidates: two independent bitmap loads per lane ----
   for (uint32_t r = 0; r < total; r += 64) {
     uint32_t o[2], glo[2], ghi[2], word[2], bit[2];
@@ -307,6 +317,36 @@ __device__ __forceinline__ void fk_global_rounds(const DevAutomaton& A, const Sc
         if (a.debug & 2u) { local_count++; continue; }
 #endif
         fk_push<IMODE, QK>(A, sm, a, warp, a0, pair_v0 + o[u], glo[u], ghi[u], local_count);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Second level = the bitmaps in shared memory (T2M = 0: needle sets beyond the exact table, q <= 4), candidates compacted as
+// above and tested 32 at a time, one per lane: with 10^4 needles several per cent of the positions pass the first level (C3:
+// 6 %, ~60 per pair), and popping them lane by lane costs the warp max-over-lanes rounds of one candidate each.
+template <int QK, bool FOLD, int IMODE>
+__device__ __forceinline__ void fk_shared_rounds(const DevAutomaton& A, const ScanArgs& a, FilterSmem* sm, uint32_t m, uint32_t incl, uint32_t total, uint32_t win_s,
+                                                 uint32_t cand_s, uint32_t t2_s, uint32_t lane, uint32_t warp, uint32_t a0, uint64_t pair_v0, unsigned long long& local_count) {
+  fk_scatter(m, incl, cand_s, lane);
+  for (uint32_t r = 0; r < total; r += 32) {
+    const uint32_t idx = r + lane;
+    if (idx < total) {
+      unsigned short ov;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ov) : "r"(cand_s + (idx << 1)));
+      const uint32_t o = ov;
+      uint32_t g;
+      if (fk_phase_a<QK, 0, FOLD>(A, win_s, t2_s, o, &g)) {
+#if FK_DEBUG
+        if (a.debug & 2u) { local_count++; continue; }
+#endif
+        uint32_t raw_hi = 0;
+        if (IMODE < 0) {
+          const uint32_t wb = win_s + (o & ~3u) + 4u;
+          raw_hi = __funnelshift_r(lds32(wb), lds32(wb + 4u), (o & 3u) * 8u);
+        }
+        fk_push<IMODE, QK>(A, sm, a, warp, a0, pair_v0 + o, g, raw_hi, local_count);
       }
     }
     __syncwarp();
@@ -434,20 +474,36 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       // ---- second level in global memory: compact the warp's candidates, look them up 64 at a time ----------------------
       const uint32_t cand_s = t2_s + warp * (FK_CAND * 2u);   // (sm->g.cand[warp]: the T2 region starts with the candidate lists)
       const uint64_t rel0 = v_begin + tile_rel + pair_rel;   // virtual index of the window's first byte
-      if (__any_sync(0xFFFFFFFFu, m != 0)) {
-        uint32_t total = __popc(m);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, d);
-        if (total <= FK_CAND) {
-          fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, m, win_s, cand_s, lane, warp, a0, rel0, local_count);
-        } else {                                           // more than the list holds: a quarter of the positions at a time (<= 256 each)
+      uint32_t incl;
+      const uint32_t total = fk_scan(m, lane, &incl);
+      if (total <= FK_CAND) {
+        fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, m, incl, total, win_s, cand_s, lane, warp, a0, rel0, local_count);
+      } else {                                             // more than the list holds: a quarter of the positions at a time (<= 256 each)
 #pragma unroll 1
-          for (uint32_t part = 0; part < 4; part++)
-            fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, m & (0xFFu << (8 * part)), win_s, cand_s, lane, warp, a0, rel0, local_count);
+        for (uint32_t part = 0; part < 4; part++) {
+          const uint32_t mp = m & (0xFFu << (8 * part));
+          uint32_t ip;
+          const uint32_t tp = fk_scan(mp, lane, &ip);
+          fk_global_rounds<QK, FOLD, IMODE>(A, a, sm, mp, ip, tp, win_s, cand_s, lane, warp, a0, rel0, local_count);
         }
       }
     } else {
-      // ---- every lane pops its own candidate bits and tests them against T2 -------------------------------
+      // ---- second level in shared memory -------------------------------------------------------------------------------------
+      // Bitmaps (T2M = 0, needle sets beyond the exact table): 10^4 needles pass several per cent of the positions at the first
+      // level -- a few per lane and pair, unevenly spread -- so the warp compacts them and tests 32 at a time (C3: -10 %).  When
+      // there are more than the list holds (4 x 10^4 needles: ~6 per lane) every lane is busy anyway and pops its own.
+      bool popped = false;
+      if (T2M == 0) {
+        uint32_t incl;
+        const uint32_t total = fk_scan(m, lane, &incl);
+        if (total <= FK_CAND0) {
+          const uint32_t cand_s = smem0 + (uint32_t)offsetof(FilterSmem, cand0) + warp * (FK_CAND0 * 2u);
+          if (total) fk_shared_rounds<QK, FOLD, IMODE>(A, a, sm, m, incl, total, win_s, cand_s, t2_s, lane, warp, a0, v_begin + tile_rel + pair_rel, local_count);
+          popped = true;
+        }
+      }
+      if (popped) m = 0;
+      // every lane pops its own candidate bits and tests them against T2 (exact table: candidates are rare)
       while (m) {
         uint32_t P;
         asm("bfind.u32 %0, %1;" : "=r"(P) : "r"(m));         // highest candidate position

@@ -113,7 +113,7 @@ struct HostAutomaton {
   std::vector<uint8_t> tails;                   // tail bytes of the simple jump slots
   std::vector<uint32_t> filter;                 // FILTER_WORDS, bank-replicated
   std::vector<uint32_t> filter2;                // T2_WORDS: bitmap, or exact key buckets when t2_exact
-  std::vector<uint32_t> gbits; uint32_t gbits_log2 = 0;   // q > 4: second level in global memory (2^gbits_log2 bits)
+  std::vector<uint32_t> gbits; uint32_t gbits_log2 = 0;   // q > 4: second level in global memory (2^gbits_log2 bits); q = 4 with bitmap T2: third level (prefix keys, gp_hash)
   bool ic_fold_ok = true;                       // IgnoreCase: the case variants of every needle's first code points fit the cells (one-pass scan)
   uint32_t t2_exact = 0, t2_empty_key = 0xFFFFFFFFu;
   uint32_t filter_keys = 0;                     // distinct q-grams
@@ -233,6 +233,11 @@ AM_HD_DECL uint32_t gq_hash(uint32_t lo, uint32_t hi) {
   h ^= h >> 15;
   return h * HASH_MUL;
 }
+// q = 4 images whose second level is the three shared-memory bitmaps also carry a THIRD level in global memory: a bitmap over the
+// needles' (folded) prefixes of min(length, 8) bytes, keyed with that length -- closed needles of 4 .. 7 bytes and the 8-byte
+// prefixes of the longer ones.  verify_kernel tests a survivor's eight carried text bytes against it (five independent loads) before
+// it decodes or lowers anything: at 10^4 needles five survivors in six are false positives of the 32 KiB bitmaps.
+AM_HD_DECL uint32_t gp_hash(uint32_t lo, uint32_t hi, uint32_t len) { return gq_hash(lo, hi + len * 0x85EBCA6Bu); }
 AM_HD_DECL uint32_t t2a_bit(uint32_t g4) { return (g4 * HASH_MUL2) >> (32 - T2A_LOG2); }
 AM_HD_DECL uint32_t t2b_bit(uint32_t g4, uint32_t b4) { return ((g4 * HASH_MUL2) ^ (b4 * HASH_MUL)) >> (32 - T2B_LOG2); }
 AM_HD_DECL uint32_t t2c_bit(uint32_t g4, uint32_t b4) { return ((g4 ^ (b4 * 0x01000193u)) * HASH_MUL3) >> (32 - T2C_LOG2); }

@@ -16,28 +16,28 @@ namespace am {
 template <int MODE, bool LOWER>
 __global__ void __launch_bounds__(256) verify_kernel(const __grid_constant__ DevAutomaton A, const __grid_constant__ ScanArgs a) {
   __shared__ unsigned long long red[8];
-  __shared__ unsigned long long start[1025];                   // start[r]: index of region r's first survivor in the concatenation of the regions
+  // Block b works on region b mod R -- the survivors filter_kernel's CTA (b mod R) listed -- together with the other blocks of
+  // that region: no prefix over the regions, no search for "the region that holds survivor k".  The regions hold similar
+  // numbers of survivors (every CTA of the scan reads the same share of the text).
   const uint32_t R = a.surv_regions;
-  if (threadIdx.x == 0) {
-    unsigned long long acc = 0, mx = 0, total = 0;
-    for (uint32_t r = 0; r < R; r++) {
-      const unsigned long long c = a.surv_counts[r];
-      start[r] = acc;
-      acc += c < a.surv_cap_cta ? c : a.surv_cap_cta;          // (a region that overflowed holds its first surv_cap_cta survivors)
-      total += c; if (c > mx) mx = c;
+  const uint32_t region = blockIdx.x % R, part = blockIdx.x / R, parts = (gridDim.x - region + R - 1) / R;   // blocks region, region + R, ... share it
+  const unsigned long long listed = a.surv_counts[region];
+  const unsigned long long n = listed < a.surv_cap_cta ? listed : a.surv_cap_cta;   // (a region that overflowed holds its first surv_cap_cta survivors)
+  if (blockIdx.x == 0 && threadIdx.x < 32) {                   // the totals the host reads: see ScanArgs::surv_count
+    unsigned long long mx = 0, total = 0;
+    for (uint32_t r = threadIdx.x; r < R; r += 32) { const unsigned long long c = a.surv_counts[r]; total += c; mx = c > mx ? c : mx; }
+    for (int o = 16; o > 0; o >>= 1) {
+      total += __shfl_down_sync(0xFFFFFFFFu, total, o);
+      const unsigned long long m2 = __shfl_down_sync(0xFFFFFFFFu, mx, o); mx = m2 > mx ? m2 : mx;
     }
-    start[R] = acc;
-    if (blockIdx.x == 0) { a.surv_count[0] = mx * R; atomicAdd(a.surv_count + 1, total); }
+    if (threadIdx.x == 0) { a.surv_count[0] = mx * R; atomicAdd(a.surv_count + 1, total); }
   }
-  __syncthreads();
-  const unsigned long long n = start[R];
   const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
+  const ulonglong2* list = a.surv + (uint64_t)region * a.surv_cap_cta;
   unsigned long long local_count = 0;
-  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+  for (unsigned long long k = (unsigned long long)part * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)parts * blockDim.x) {
     if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
-    uint32_t lo = 0, hi = R;                                   // the region that holds survivor k
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (start[mid] <= k) lo = mid; else hi = mid; }
-    const ulonglong2 e = a.surv[(uint64_t)lo * a.surv_cap_cta + (k - start[lo])];   // {virtual index = a0 + text index, eight text bytes}
+    const ulonglong2 e = list[k];                              // {virtual index = a0 + text index, eight text bytes}
     if (e.x < a0) continue;                                    // bytes of the first granule that precede the text
     fk_deep_verify<MODE, LOWER>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
   }

@@ -191,7 +191,7 @@ def test_filter_has_no_false_negatives(oracle):
             starts = np.unique(want["pos"] - np.array([len(nb[v]) for v in want["value"]], dtype=np.int64))
             for align in (0, 1):
                 flags = m.host_filter_flags(raw, align)
-                assert starts[(flags[starts] & 3) != 3].size == 0, (name, align)
+                assert starts[(flags[starts] & 7) != 7].size == 0, (name, align)
                 assert float((flags & 1).mean()) < 0.05
             continue
         if isinstance(alpha, bytes):
@@ -209,7 +209,7 @@ def test_filter_has_no_false_negatives(oracle):
         starts = np.unique(want["pos"] - np.array([len(nb[v]) for v in want["value"]], dtype=np.int64))
         for align in (0, 1):
             flags = m.host_filter_flags(hay, align)
-            missed = starts[(flags[starts] & 3) != 3]
+            missed = starts[(flags[starts] & 7) != 7]
             assert missed.size == 0, (name, align, missed[:5])
             rate1, rate2 = float((flags & 1).mean()), float(((flags & 3) == 3).mean())
             assert rate2 <= rate1 <= 1.0
@@ -289,5 +289,39 @@ def test_filter_covers_length_changing_variants(oracle, lower_dense):
     starts = np.array(sorted(starts), dtype=np.int64)
     for align in (0, 1):
         flags = m.host_filter_flags(hay, align)
-        missed = starts[(flags[starts] & 3) != 3]
+        missed = starts[(flags[starts] & 7) != 7]
         assert missed.size == 0, (align, missed[:5])
+
+
+def test_third_level_prefix_bitmap(oracle, lower_dense):
+    """q = 4 images whose second level is the three shared-memory bitmaps carry a third level in global memory: the (folded)
+    prefixes of min(length, 8) bytes of every needle variant (am_build.cpp, gp_hash), tested by verify_kernel before it decodes
+    anything.  Host model, C3-like: lower-case needles with non-ASCII code points, IgnoreCase, on mixed-case UTF-8 text: every
+    start of an oracle `runLower` match passes all three levels, and the third level rejects most of what the second lets by."""
+    from alfred_margaret_b200 import automaton, synth, workloads
+    needles = workloads.c3_needles(5000)
+    hay = workloads.c3_unit(needles)[: 1 << 20].copy()
+    while (hay[-1] & 0xC0) == 0x80 or hay[-1] >= 0xC0: hay = hay[:-1]          # end on a code point boundary
+    want = oracle.Machine(needles).find_all(hay, cs=1, lower=lower_dense, cap=1 << 22)
+    assert len(want) > 200
+    is_lead = (hay & 0xC0) != 0x80
+    lead_index = np.flatnonzero(is_lead)
+    cp_of_byte = np.cumsum(is_lead) - 1
+    n_cps = [len(n.decode("utf-8")) for n in needles]
+    starts = np.unique(np.array([int(lead_index[cp_of_byte[pos - 1] + 1 - n_cps[v]]) for pos, v in zip(want["pos"].tolist(), want["value"].tolist())], dtype=np.int64))
+    m = automaton.AcMachine([(n, i) for i, n in enumerate(needles)], case_sensitivity=1, device=-2, force_kernel=2)
+    assert m.info()["kernel_kind"] == 2
+    for align in (0, 1):
+        flags = m.host_filter_flags(hay, align)
+        missed = starts[(flags[starts] & 7) != 7]
+        assert missed.size == 0, (align, missed[:5])
+        two, three = float(((flags & 3) == 3).mean()), float(((flags & 7) == 7).mean())
+        assert three < 0.4 * two, (two, three)
+    # CaseSensitive image of a large set: same property on plain bytes
+    nb = synth.random_needles(6000, 43, 4, 12)
+    h2 = synth.fill_host(0, 1 << 18, 9, synth.AZ)
+    synth.plant_host(h2, 0, 10, nb, block=512)
+    w2 = oracle.Machine(nb).find_all(h2, cap=1 << 22)
+    s2 = np.unique(w2["pos"] - np.array([len(nb[v]) for v in w2["value"]], dtype=np.int64))
+    f2 = automaton.AcMachine([(n, i) for i, n in enumerate(nb)], device=-2).host_filter_flags(h2, 0)
+    assert s2[(f2[s2] & 7) != 7].size == 0 and float(((f2 & 7) == 7).mean()) < float(((f2 & 3) == 3).mean())
