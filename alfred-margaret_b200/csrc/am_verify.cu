@@ -35,11 +35,49 @@ __global__ void __launch_bounds__(256) verify_kernel(const __grid_constant__ Dev
   const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(a.text) & 15);
   const ulonglong2* list = a.surv + (uint64_t)region * a.surv_cap_cta;
   unsigned long long local_count = 0;
-  for (unsigned long long k = (unsigned long long)part * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)parts * blockDim.x) {
-    if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
-    const ulonglong2 e = list[k];                              // {virtual index = a0 + text index, eight text bytes}
-    if (e.x < a0) continue;                                    // bytes of the first granule that precede the text
-    fk_deep_verify<MODE, LOWER>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
+  if (fk_has_level3(A)) {
+    // Images with a third filter level (C3): nine survivors in ten end at that check, and the rest -- scattered over the lanes --
+    // would run the divergent verification three lanes to a warp.  So a batch is CHECKED one survivor per thread, those that
+    // pass are queued in shared memory, and a full block's worth of them is VERIFIED one per thread (all lanes busy).
+    __shared__ ulonglong2 q[2 * 256];
+    __shared__ uint32_t q_n;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) q_n = 0;
+    __syncthreads();
+    for (unsigned long long base = (unsigned long long)part * 256; base < n; base += (unsigned long long)parts * 256) {   // (uniform over the block)
+      if (MODE == MODE_ANY && __syncthreads_or(*reinterpret_cast<volatile int*>(a.d_flag))) break;
+      const unsigned long long k = base + tid;
+      if (k < n) {
+        const ulonglong2 e = list[k];                            // {virtual index = a0 + text index, eight text bytes}
+        if (e.x >= a0 && fk_level3_pass(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32))) q[atomicAdd(&q_n, 1u)] = e;
+      }
+      __syncthreads();
+      const uint32_t waiting = q_n;
+      __syncthreads();                                           // (everyone has read the count before the next batch adds to it)
+      if (waiting >= 256) {
+        const ulonglong2 e = q[tid];
+        fk_deep_verify<MODE, LOWER, false>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
+        const bool more = 256 + tid < waiting;
+        ulonglong2 mv = make_ulonglong2(0, 0);
+        if (more) mv = q[256 + tid];
+        __syncthreads();
+        if (more) q[tid] = mv;
+        if (tid == 0) q_n = waiting - 256;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    if (tid < q_n) {
+      const ulonglong2 e = q[tid];
+      fk_deep_verify<MODE, LOWER, false>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
+    }
+  } else {
+    for (unsigned long long k = (unsigned long long)part * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)parts * blockDim.x) {
+      if (MODE == MODE_ANY && *reinterpret_cast<volatile int*>(a.d_flag)) break;
+      const ulonglong2 e = list[k];                              // {virtual index = a0 + text index, eight text bytes}
+      if (e.x < a0) continue;                                    // bytes of the first granule that precede the text
+      fk_deep_verify<MODE, LOWER, false>(A, a, e.x - a0, (uint32_t)e.y, (uint32_t)(e.y >> 32), local_count);
+    }
   }
   if (MODE == MODE_COUNT) {
     for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xFFFFFFFFu, local_count, o);

@@ -117,7 +117,28 @@ __device__ __forceinline__ void fk_report_state(const DevAutomaton& A, const Sca
 // text at i.  No failure links are needed because every start position is tried (failure-less, position-parallel
 // formulation of Aho-Corasick).  The jump table maps the q-gram to its trie state -- or, when a single needle path
 // hangs below it (nearly always), to that path's tail, which is compared with the text in one go.
-template <int MODE, bool LOWER>
+// Third filter level (gp_hash, am_build.cpp; images with q = 4 and the bitmap second level): is one of the text's (folded) prefixes of
+// 4 .. 8 bytes at i a closed needle resp. the 8-byte prefix of a longer one?  Five independent loads from an L2-resident bitmap,
+// before anything is decoded or lowered.  b_lo, b_hi: the eight text bytes at i (as they stand in the text).
+__device__ __forceinline__ bool fk_has_level3(const DevAutomaton& A) { return A.q == 4 && !A.t2_exact && A.gbits_shift < 32; }
+__device__ __forceinline__ bool fk_level3_pass(const DevAutomaton& A, const ScanArgs& a, uint64_t i, uint32_t b_lo, uint32_t b_hi) {
+  if (!fk_has_level3(A) || i + 8 > a.text_len) return true;   // (carried bytes that run past the text decide nothing)
+  uint32_t f_lo = b_lo, f_hi = b_hi;
+  if (A.ignore_case) { f_lo |= FOLD_MASK; f_hi |= FOLD_MASK; }
+  uint32_t bit[5], word[5];
+#pragma unroll
+  for (uint32_t L = 4; L <= 8; L++) {
+    const uint32_t h = L == 4 ? 0u : L == 8 ? f_hi : f_hi & ((1u << (8 * (L - 4))) - 1u);
+    bit[L - 4] = gp_hash(f_lo, h, L) >> A.gbits_shift;
+    word[L - 4] = __ldg(A.gbits + (bit[L - 4] >> 5));
+  }
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) any |= word[k] >> (bit[k] & 31);
+  return (any & 1u) != 0;
+}
+
+template <int MODE, bool LOWER, bool CHECK_L3 = true>
 __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const ScanArgs& a, uint64_t i, uint32_t b_lo, uint32_t b_hi, unsigned long long& local_count) {
   // i: text index of the survivor; b_lo, b_hi: the eight text bytes there, carried from the scan kernel's window (bytes beyond
   // the text are arbitrary: every use below is bounded by text_len)
@@ -126,23 +147,7 @@ __device__ __forceinline__ void fk_deep_verify(const DevAutomaton& A, const Scan
   const uint32_t q = A.q;
   uint32_t g_lo = 0, g_hi = 0;
   const bool carried = i + 8 <= a.text_len;                   // (else the carried bytes run past the text: read it instead)
-  if (carried && q == 4 && !A.t2_exact && A.gbits_shift < 32) {
-    // third filter level (gp_hash, am_build.cpp): is one of the text's (folded) prefixes of 4 .. 8 bytes here a closed needle resp. the
-    // 8-byte prefix of a longer one?  Five independent loads from an L2-resident bitmap, before anything is decoded or lowered.
-    uint32_t f_lo = b_lo, f_hi = b_hi;
-    if (A.ignore_case) { f_lo |= FOLD_MASK; f_hi |= FOLD_MASK; }
-    uint32_t bit[5], word[5];
-#pragma unroll
-    for (uint32_t L = 4; L <= 8; L++) {
-      const uint32_t h = L == 4 ? 0u : L == 8 ? f_hi : f_hi & ((1u << (8 * (L - 4))) - 1u);
-      bit[L - 4] = gp_hash(f_lo, h, L) >> A.gbits_shift;
-      word[L - 4] = __ldg(A.gbits + (bit[L - 4] >> 5));
-    }
-    uint32_t any = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) any |= word[k] >> (bit[k] & 31);
-    if (!(any & 1u)) return;
-  }
+  if (CHECK_L3 && !fk_level3_pass(A, a, i, b_lo, b_hi)) return;
   // CaseSensitive: the carried bytes ARE the text; the stream starts behind them.  IgnoreCase in one pass: `runLower` lowers
   // every code point, so the carried bytes seed the lowering stream (ASCII is lowered in place, anything else decoded).
   uint32_t have = (!LOWER && carried) ? 8u : 0u;              // text bytes [0, have) are compared straight from (b_lo, b_hi)

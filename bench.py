@@ -624,12 +624,14 @@ def run_ours(args):
         pbuf[:] = hbuf[:P]
         ps = _ffi.U8Slice(pbuf.ctypes.data, 0, P)
         step_e2e(ps)
-        t0 = time.perf_counter()
-        for _ in range(2):
+        tp = []
+        for _ in range(3):
+            t0 = time.perf_counter()
             step_e2e(ps)
-        dtp = (time.perf_counter() - t0) / 2
+            tp.append(time.perf_counter() - t0)
+        dtp = sorted(tp)[1]                                 # median of three: page-locking a GiB in place costs 30 .. 500 ms from call to call
         pageable = {"value": P / dtp / 1e9, "unit": "GB/s", "bytes": P, "ms_per_step": dtp * 1e3,
-                    "how": "numpy (pageable) buffer; am_find_all page-locks texts >= 256 MiB in place for the call (cudaHostRegister) and unlocks them after"}
+                    "how": "numpy (pageable) buffer; am_find_all page-locks texts >= 256 MiB in place for the call (cudaHostRegister) and unlocks them after; median of 3 calls", "ms_all": [round(x * 1e3, 2) for x in tp]}
     parity_all = all_true(torch, dist, world, parity_all and parity_e2e)
 
     # ---- CPU baseline (rank 0, single GPU only): the reference harness's protocol ---------------------------------------------
