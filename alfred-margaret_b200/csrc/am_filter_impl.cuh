@@ -364,6 +364,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
   constexpr bool S2 = QK == 4;
   constexpr int COPIES = QK > 4 ? 1 : S2 ? filter_copies_s2(T2M == 1) : FK_COPIES_S1;
   static_assert(T2M != 2 || QK > 4, "the global second level serves the long q-grams");
+  // Exact second level (survivors are rare: one in 2 000 positions at C2): look at the survivor stage once per TWO pairs -- one copy
+  // of the flush / verification code in the unrolled loop instead of two (C2: -1.5 % COUNT, -2.2 % EMIT).  Sets that survive more
+  // often would overflow the stage into the in-place verification (4 x 10^4 needles: +20 %), they look after every pair.
+  constexpr bool FLUSH_PER_TWO = T2M == 1;
   constexpr bool TAIL8 = QK > 4 || IMODE < 0;                // the window carries two words beyond the pair (long q-grams; the list form's eight text bytes per survivor)
 
   // ---- stage the filter bitmap and T2 into shared memory with TMA bulk copies -----------------------
@@ -524,7 +528,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
         }
       }
     }
-    fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, FK_DRAIN_AT, local_count);   // only when a full round of survivors waits
+    if (!FLUSH_PER_TWO) fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, FK_DRAIN_AT, local_count);   // only when a full round of survivors waits
+    else __syncwarp();                                       // (lanes still popping candidates read the window the next pair overwrites)
   };
 
   static_assert(FK_PAIRS % 2 == 0, "the pair loop is unrolled by two");
@@ -556,6 +561,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) filter_kernel(const __grid_cons
       g_next += pair + 2 < FK_PAIRS ? 64 : tile_stride_granules - (FK_PAIRS - 1) * 64;   // next even pair: same chunk, or this warp's chunk in the CTA's next tile
       load_pair(g_next, cA, cB, tC);                       // beyond the CTA's last tile this is a clamped, unused load
       process_pair(nA, nB, tN, tile_rel, chunk_rel + (uint32_t)pair * 1024u + 1024u);
+      if (FLUSH_PER_TWO) fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, FK_DRAIN_AT, local_count);
     }
   }
   fk_flush<IMODE, QK>(A, sm, a, warp, lane, a0, 1, local_count);

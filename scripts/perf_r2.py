@@ -86,6 +86,35 @@ if "C5" in which:
         measure("100k needles 8-16 B (q = 8)", automaton.AcMachine([(x, i) for i, x in enumerate(nd)]), dev.data_ptr(), n)
     del dev
 
+if "robust" in which:
+    # the C2 automaton (and an English-word one) on texts that are NOT uniform random letters: throughput must degrade gracefully
+    n = 1 * GIB
+    rng = np.random.default_rng(7)
+    needles = workloads.c2_needles()
+    m = automaton.AcMachine([(x, i) for i, x in enumerate(needles)])
+    def tile_to_dev(unit):
+        reps = n // unit.size
+        dev = torch.empty(reps * unit.size, dtype=torch.uint8, device="cuda")
+        dev.view(reps, unit.size).copy_(torch.from_numpy(unit).cuda().unsqueeze(0).expand(reps, unit.size))
+        return dev
+    # (1) dense: a needle planted every 64 bytes (64x C2's match density)
+    unit = synth.fill_host(0, 16 << 20, 43, synth.AZ); synth.plant_host(unit, 0, 44, needles, block=64)
+    dev = tile_to_dev(unit); measure("robust: C2 needles, a plant per 64 B", m, dev.data_ptr(), dev.numel()); del dev
+    # (2) skewed letter frequencies (English-like unigram distribution) + spaces
+    freq = np.array([8.2,1.5,2.8,4.3,12.7,2.2,2.0,6.1,7.0,0.15,0.77,4.0,2.4,6.7,7.5,1.9,0.095,6.0,6.3,9.1,2.8,0.98,2.4,0.15,2.0,0.074, 18.0])
+    alpha = np.frombuffer(synth.AZ + b" ", dtype=np.uint8)
+    unit = alpha[rng.choice(27, size=16 << 20, p=freq / freq.sum())].copy()
+    dev = tile_to_dev(unit); measure("robust: C2 needles, English letter frequencies", m, dev.data_ptr(), dev.numel()); del dev
+    # (3) adversarial: the text is made of the needles' own 4-gram prefixes (every position passes the first level)
+    pre = np.frombuffer(b"".join(x[:4] for x in needles), dtype=np.uint8)
+    unit = np.tile(pre, (16 << 20) // pre.size + 1)[: 16 << 20].copy()
+    dev = tile_to_dev(unit); measure("robust: text = the needles' 4-gram prefixes", m, dev.data_ptr(), dev.numel()); del dev
+    # (4) adversarial: one letter repeated, against needles of that letter (survivor flood -> hand-over to the walk kernel)
+    ma = automaton.AcMachine([(b"a" * k, k) for k in range(4, 12)])
+    dev = torch.full((n,), ord("a"), dtype=torch.uint8, device="cuda")
+    measure("robust: 'aaaa..' vs needles a^4..a^11 (count only)", ma, dev.data_ptr(), n // 16)
+    del dev
+
 if "C4" in which:
     needles, repls = workloads.c4_pairs()
     n = 2 * GIB
