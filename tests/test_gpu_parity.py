@@ -396,6 +396,31 @@ def test_config3_downscaled_ignore_case(am, oracle, lower_dense):
     assert m.count_matches(hay) == len(want)
 
 
+def test_large_set_three_filter_levels(am, oracle, lower_dense):
+    """Needle sets beyond the exact second level on 4-grams (> 2 048 distinct q-grams): warp-cooperative bitmap level, the third
+    level in global memory (prefixes of min(length, 8) bytes, every case variant) and verify_kernel's queue of the survivors that
+    pass it.  IgnoreCase with non-ASCII needles on mixed-case UTF-8 text (C3's shape, 6 000 needles) and the same machine
+    CaseSensitive; count, full list and containsAny (match present / absent: the queue's block-wide early exit)."""
+    from alfred_margaret_b200 import workloads
+    needles = [n.decode("utf-8") for n in workloads.c3_needles(6000)]
+    hay = workloads.c3_unit([n.encode("utf-8") for n in needles])[: 3 << 20].copy()
+    while (hay[-1] & 0xC0) == 0x80 or hay[-1] >= 0xC0: hay = hay[:-1]          # end on a code point boundary
+    hb = hay.tobytes()
+    om = oracle.Machine(needles)
+    m = machine(am, needles, cs=1)
+    assert m.info()["kernel_kind"] == 2
+    for cs in (1, 0):
+        want = om.find_all(hb, cs=cs, lower=lower_dense if cs else None, cap=1 << 22)
+        assert len(want) > (300 if cs else 5)
+        got = m.find_all(hb, case=cs)
+        assert len(got) == len(want) and np.array_equal(got["end_pos"].astype(np.int64), want["pos"]) and np.array_equal(got["needle_id"].astype(np.int64), want["value"]), cs
+        assert m.count_matches(hb, case=cs) == len(want)
+        assert m.contains_any(hb, case=cs) is True
+    quiet = ("zq " * 300000).encode()                          # no needle holds "zq ": every survivor dies in the levels or the check
+    assert len(om.find_all(quiet, cs=1, lower=lower_dense)) == 0
+    assert m.contains_any(quiet, case=1) is False and m.count_matches(quiet, case=1) == 0
+
+
 def test_config5_downscaled_many_needles(am, oracle, torch_cuda):
     """BASELINE.json config 5 down-scaled: 100 000 needles (6-16 B), 32 MiB haystack in 4 shards with halos;
     per-shard lists concatenate to the single-shard list; counts all-gathered (here: summed) match."""
