@@ -684,7 +684,7 @@ def run_ours(args):
                        "kernel": {1: "walk", 2: "qgram-filter"}[info["kernel_kind"]], "host_affinity": affinity},
             "matches_per_step": n_total, "matches_per_s": n_total / (ms_step * 1e-3),
             "e2e": {"value": world * E / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": E, "d2h_bytes_per_step": n_e2e * 16 + 16,
-                    "ms_per_step": e2e_ms, "wall_ms_per_step": wall_e2e, "api": "am_find_all (host slice in, am_match[] out)", "memory": "pinned (cudaHostAlloc via torch), first-touched on the GPU's NUMA node",
+                    "ms_per_step": e2e_ms, "wall_ms_per_step": wall_e2e, "api": "am_find_all (host slice in, am_match[] out)", "memory": "pinned (cudaHostAlloc via torch), allocated after the rank was bound with nvmlDeviceSetCpuAffinity (config.host_affinity: a no-op on a box that exposes one NUMA node / numa_node -1)",
                     "input": "the whole shard" if E == B else "first %d MiB of the shard (host memory per rank)" % (E >> 20), "pageable": pageable},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": c.peak, "unit": "GB/s", "frac": achieved / c.peak, "traffic": traffic, "traffic_source": traffic_src,
