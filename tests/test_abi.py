@@ -325,3 +325,46 @@ def test_third_level_prefix_bitmap(oracle, lower_dense):
     s2 = np.unique(w2["pos"] - np.array([len(nb[v]) for v in w2["value"]], dtype=np.int64))
     f2 = automaton.AcMachine([(n, i) for i, n in enumerate(nb)], device=-2).host_filter_flags(h2, 0)
     assert s2[(f2[s2] & 7) != 7].size == 0 and float(((f2 & 7) == 7).mean()) < float(((f2 & 3) == 3).mean())
+
+
+def test_haskell_shim_imports_agree_with_the_header():
+    """GHC is not installed here, so the shim under alfred-margaret_b200/haskell/ cannot be compiled; what CAN be checked
+    is that every `foreign import ccall` names a symbol the header declares, with the same number of arguments, a pointer
+    wherever the C parameter is one (every struct travels by pointer: GHC's FFI cannot pass one by value) and an integer
+    status as the result -- and that the modules keep the reference's export lists (Automaton.hs:32-44, Searcher.hs:14-27,
+    Replacer.hs:14-27, Splitter.hs:13-22)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "am_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|void|uint64_t|size_t|const char \*)\s*\b(am_\w+)\s*\(([^;{]*?)\)\s*;", hdr):
+        params = [x.strip() for x in m.group(3).split(",") if x.strip() and x.strip() != "void"]
+        protos[m.group(2)] = (m.group(1), params)
+    hs_dir = os.path.join(ROOT, "alfred-margaret_b200", "haskell", "Data", "Text", "AhoCorasick")
+    ffi = open(os.path.join(hs_dir, "FFI.hs")).read()
+    imports = re.findall(r'foreign import ccall\s+(?:safe|unsafe)?\s*"(&?)(am_\w+)"\s*\n\s*\w+\s*::\s*([^\n]+)', ffi)
+    assert len(imports) >= 12
+    for addr, name, sig in imports:
+        assert name in protos, name
+        ret, params = protos[name]
+        if addr:                                               # `&am_x_free`: a finalizer, FunPtr (Ptr T -> IO ())
+            assert sig.strip().startswith("FunPtr") and len(params) == 1 and ret == "void", name
+            continue
+        parts = [x.strip() for x in re.split(r"->", sig)]
+        args, res = parts[:-1], parts[-1]
+        assert len(args) == len(params), (name, args, params)
+        for h, c in zip(args, params):
+            assert ("Ptr" in h) == ("*" in c), (name, h, c)     # pointers where C has pointers, scalars where it has scalars
+        assert res == {"int": "IO CInt", "void": "IO ()", "size_t": "IO CSize"}[ret], (name, res)
+    exports = {
+        "Automaton.hs": ["AcMachine", "build", "runText", "runLower", "runWithCase", "Match", "Next"],
+        "Searcher.hs": ["Searcher", "build", "buildWithValues", "containsAny", "containsAll", "setCaseSensitivity", "caseSensitivity", "needles"],
+        "Replacer.hs": ["Replacer", "build", "compose", "mapReplacement", "run", "runWithLimit", "setCaseSensitivity"],
+        "Splitter.hs": ["Splitter", "build", "split", "splitIgnoreCase", "splitReverse", "splitReverseIgnoreCase"],
+    }
+    for fn, names in exports.items():
+        src = open(os.path.join(hs_dir, fn)).read()
+        head = src[: src.index(" where")]
+        for n in names:
+            assert re.search(r"\b%s\b" % n, head), (fn, n)
+    assert not os.path.exists(os.path.join(ROOT, "alfred-margaret_b200", "haskell", "cbits"))   # no C glue: nothing is passed by value
