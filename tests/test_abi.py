@@ -368,3 +368,12 @@ def test_haskell_shim_imports_agree_with_the_header():
         for n in names:
             assert re.search(r"\b%s\b" % n, head), (fn, n)
     assert not os.path.exists(os.path.join(ROOT, "alfred-margaret_b200", "haskell", "cbits"))   # no C glue: nothing is passed by value
+    # the Storable instances and status constants of FFI.hs against the C side
+    from alfred_margaret_b200 import _ffi
+    import ctypes
+    for hs_type, c_type in (("U8Slice", _ffi.U8Slice), ("AmMatch", _ffi.Match), ("AmLowerPair", _ffi.LowerPair)):
+        m = re.search(r"instance Storable %s where\s*\n\s*sizeOf _ = (\d+)\s*\n\s*alignment _ = (\d+)" % hs_type, ffi)
+        assert m and int(m.group(1)) == ctypes.sizeof(c_type) and int(m.group(2)) == ctypes.alignment(c_type), hs_type
+    enum = dict(re.findall(r"\b(AM_\w+)\s*=\s*(-?\d+)", hdr))
+    assert re.search(r"amOk = %s\b" % enum["AM_OK"], ffi) and re.search(r"amEOverflow = %s\b" % enum["AM_E_OVERFLOW"], ffi)
+    assert re.search(r"caseToC CaseSensitive = %s\b" % enum["AM_CASE_SENSITIVE"], ffi) and re.search(r"caseToC IgnoreCase = %s\b" % enum["AM_IGNORE_CASE"], ffi)
