@@ -1,6 +1,7 @@
 {-# LANGUAGE BangPatterns #-}
 {-# LANGUAGE ForeignFunctionInterface #-}
 {-# LANGUAGE MagicHash #-}
+{-# LANGUAGE UnboxedTuples #-}
 -- | Raw bindings to libam_b200.so (include/am_b200.h, ABI version 2) and the marshalling helpers every wrapper
 -- module uses.
 --
@@ -31,6 +32,8 @@ import Foreign.Marshal (alloca, allocaBytes, withArrayLen)
 import Foreign.Ptr (FunPtr, Ptr, castPtr, nullPtr)
 import Foreign.Storable (Storable (..))
 import System.IO.Unsafe (unsafePerformIO)
+import GHC.Exts (touch#)
+import GHC.IO (IO (..))
 
 import qualified Data.Char as Char
 import qualified Data.Text.Array as TextArray
@@ -123,6 +126,10 @@ pinText t@(Text u8data off len)
   | Utf8.isArrayPinned u8data = t
   | otherwise = Text (TextArray.run (do { dst <- TextArray.newPinned len; TextArray.copyI len dst 0 u8data off; pure dst })) 0 len
 
+-- | The array's address has crossed the FFI: the garbage collector must not free it before the call returns.
+touchArray :: TextArray.Array -> IO ()
+touchArray (TextArray.ByteArray ba#) = IO (\s -> case touch# ba# s of s' -> (# s', () #))
+
 -- | `U8Slice` of a PINNED Text (the reference's `fromText`, benchmark/rust-ffi/app/Main.hs:49-52).
 toSlice :: Text -> U8Slice
 toSlice (Text u8data off len)
@@ -136,7 +143,7 @@ withSlice text act =
   in alloca $ \p -> do
        poke p (toSlice pinned)
        r <- act p
-       TextArray.touch arr      -- keeps the ByteArray# alive until the call has returned (Data.Text.Array)
+       touchArray arr           -- keeps the ByteArray# alive until the call has returned
        pure r
 
 -- | An array of slices (needles, replacements).
@@ -145,7 +152,7 @@ withSlices texts act =
   let pinned = map pinText texts
   in withArrayLen (map toSlice pinned) $ \n p -> do
        r <- act p (fromIntegral n)
-       mapM_ (\(Text arr _ _) -> TextArray.touch arr) pinned
+       mapM_ (\(Text arr _ _) -> touchArray arr) pinned
        pure r
 
 -- | The host's `Data.Char.toLower` above ASCII as data (Utf8.lowerCodePoint, Utf8.hs:145-151, is `Char.toLower` there):
