@@ -5,6 +5,7 @@ module Data.Text.AhoCorasick.Replacer
   , setCaseSensitivity, replacerCaseSensitivity
   ) where
 
+import Control.Monad.ST (stToIO)
 import Data.Maybe (fromJust)
 import Data.Text.CaseSensitivity (CaseSensitivity (..))
 import Data.Text.Utf8 (CodeUnitIndex (..), Text (..))
@@ -91,7 +92,7 @@ runWithLimit r (CodeUnitIndex maxLength) text = unsafePerformIO $
       p <- peek outPtr
       n <- fromIntegral <$> peek outLen
       -- copy the library's buffer into a fresh ByteArray#, then release it
-      arr <- TextArray.unsafeFreeze =<< do { dst <- TextArray.new n; TextArray.copyFromPointer dst 0 p n; pure dst }
+      arr <- stToIO $ do { dst <- TextArray.new n; TextArray.copyFromPointer dst 0 p n; TextArray.unsafeFreeze dst }
       c_am_free p
       pure (Just (Text arr 0 n))
 {-# NOINLINE runWithLimit #-}
